@@ -1,0 +1,87 @@
+"""ctypes binding of ``libartspeech_b200.so`` (the C ABI in ``include/artspeech_b200.h``).
+
+There is deliberately no fallback: if the library is missing or an entry point fails the call
+raises.  The oracle under ``oracle/`` is test infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+AS_F16, AS_BF16, AS_F32 = 0, 1, 2
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SWISH, ACT_ABS = 0, 1, 2, 3, 4, 5
+
+c_i32_p = C.POINTER(C.c_int32)
+c_f32_p = C.POINTER(C.c_float)
+
+
+class ConvParams(C.Structure):
+    """Mirror of ``struct as_conv_params``."""
+    _fields_ = [
+        ("x", C.c_void_p), ("x_dtype", C.c_int32),
+        ("B", C.c_int32), ("T", C.c_int32), ("F", C.c_int32), ("Cin", C.c_int32),
+        ("x_ld", C.c_int64),
+        ("w", C.c_void_p),
+        ("ntaps", C.c_int32), ("CinP", C.c_int32), ("CoutP", C.c_int32), ("Cout", C.c_int32),
+        ("tap_dt", c_i32_p), ("tap_df", c_i32_p),
+        ("To", C.c_int32), ("Fo", C.c_int32),
+        ("bias", C.c_void_p),
+        ("res1", C.c_void_p), ("res1_dtype", C.c_int32), ("res1_ld", C.c_int64),
+        ("res2", C.c_void_p), ("res2_dtype", C.c_int32), ("res2_ld", C.c_int64),
+        ("out_scale", C.c_float),
+        ("y_raw", C.c_void_p), ("y_raw_dtype", C.c_int32), ("y_raw_ld", C.c_int64),
+        ("y_act", C.c_void_p), ("y_act_dtype", C.c_int32), ("y_act_ld", C.c_int64),
+        ("act", C.c_int32), ("slope", C.c_float),
+        ("lens", C.c_void_p),
+        ("stats", C.c_void_p),
+    ]
+
+
+class AsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol declared in include/artspeech_b200.h
+SIGNATURES = {
+    "as_version": (C.c_int, []),
+    "as_last_error": (C.c_char_p, []),
+    "as_mas_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "as_mas_maximum_path": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
+    "as_conv_tile_n": (C.c_int32, [C.c_int32]),
+    "as_conv_igemm": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load (building in-tree first when needed) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.isfile(path):
+        if not build_if_missing:
+            raise AsError(f"{path} not built; run `python -m artspeech_b200.build`")
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().as_last_error()
+        raise AsError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,498 @@
+// Implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused
+// epilogue.  One kernel family serves every dense contraction on the synthesis path
+// (SURVEY.md §10): Conv1d / polyphase ConvTranspose1d / Conv2d / Linear.
+//
+// GEMM view (per output tile): D[128 rows, BN] += sum over (tap j, channel chunk c) of
+//     A_j,c[128, BK] * W_j,c[BN, BK]^T
+// rows   = a tT x tF rectangle of output positions of one batch item (tT*tF = 128),
+// A_j,c  = the same rectangle of the channels-last input, shifted by the tap offset (dt, df):
+//          ONE 4-D TMA box per (tap, chunk); out-of-range coordinates are zero-filled by the TMA
+//          unit, which is exactly the convolution's zero padding,
+// W_j,c  = a [BN, BK] K-major box of the packed weight matrix [ntaps*CoutP, CinP].
+// Both operands use the canonical K-major 128B (BK=64) / 64B (BK=32) swizzled layout that TMA
+// writes and the UMMA shared-memory descriptor reads.  fp32 accumulators live in TMEM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
+// issuer (one lane), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace asb {
+
+constexpr int CV_THREADS = 192;
+constexpr int CV_MAX_TAPS = 32;
+
+struct ConvArgs {
+  int B, To, Fo, Cout, CoutP;
+  int tT, tF, n_ttiles, n_ftiles;
+  int ntaps, kchunks, stages;
+  int tap_dt[CV_MAX_TAPS];
+  int tap_df[CV_MAX_TAPS];
+  uint32_t idesc;
+  const float* bias;
+  const void* res1; int res1_dtype; long long res1_ld;
+  const void* res2; int res2_dtype; long long res2_ld;
+  float out_scale;
+  void* y_raw; int y_raw_dtype; long long y_raw_ld; int y_raw_vec;
+  void* y_act; int y_act_dtype; long long y_act_ld; int y_act_vec;
+  int act; float slope;
+  const int* lens;
+  float* stats;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, =1) | [32,46) SBO>>4
+//   [46,48) version=1 | [61,64) layout (2 = 128B swizzle, 4 = 64B swizzle)
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t sbo = (BK == 64 ? 1024 : 512) >> 4;  // 8 rows x row bytes
+  constexpr uint64_t layout = (BK == 64) ? 2 : 4;
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (sbo << 32) | (uint64_t(1) << 46) |
+         (layout << 61);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue store helpers: 16 consecutive channels of one row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store16(void* base, int dtype, long long off, const float (&v)[16],
+                                        int nvalid, bool vec) {
+  if (dtype == AS_F32) {
+    float* p = reinterpret_cast<float*>(base) + off;
+    if (vec && nvalid == 16) {
+      float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < nvalid) p[i] = v[i];
+    }
+  } else {
+    uint16_t* p = reinterpret_cast<uint16_t*>(base) + off;
+    if (vec && nvalid == 16) {
+      uint4* p4 = reinterpret_cast<uint4*>(p);
+      p4[0] = make_uint4(pack16(v[0], v[1], dtype), pack16(v[2], v[3], dtype),
+                         pack16(v[4], v[5], dtype), pack16(v[6], v[7], dtype));
+      p4[1] = make_uint4(pack16(v[8], v[9], dtype), pack16(v[10], v[11], dtype),
+                         pack16(v[12], v[13], dtype), pack16(v[14], v[15], dtype));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < nvalid) p[i] = to16(v[i], dtype);
+    }
+  }
+}
+
+__device__ __forceinline__ void add_res16(const void* base, int dtype, long long off, float (&v)[16],
+                                          int nvalid, bool vec) {
+  if (dtype == AS_F32) {
+    const float* p = reinterpret_cast<const float*>(base) + off;
+    if (vec && nvalid == 16) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 t = __ldg(p4 + i);
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += p[i];
+    }
+  } else {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + off;
+    if (vec && nvalid == 16) {
+      const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 t = __ldg(p4 + h);
+        uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[8 * h + 2 * i] += from16(uint16_t(w[i] & 0xFFFF), dtype);
+          v[8 * h + 2 * i + 1] += from16(uint16_t(w[i] >> 16), dtype);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += from16(p[i], dtype);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int BK>
+__global__ void __launch_bounds__(CV_THREADS)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ ConvArgs a) {
+  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int W_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int S = a.stages;
+  const uint32_t bar_base = smem_base + S * STAGE_BYTES;  // full[S], empty[S], tmem_full, slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
+  const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
+  const int b = mt;
+  const int t0 = tt * a.tT, f0 = ft * a.tF;
+  const int n0 = blockIdx.y * BN;
+  const int k_iters = a.ntaps * a.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const int tap = it / a.kchunks, kc = it - tap * a.kchunks;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        tma_load_4d(sa, &tmA, full_bar(s), kc * BK, f0 + a.tap_df[tap], t0 + a.tap_dt[tap], b);
+        tma_load_2d(sa + A_BYTES, &tmW, full_bar(s), kc * BK, tap * a.CoutP + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint64_t da = make_smem_desc<BK>(sa);
+        const uint64_t db = make_smem_desc<BK>(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 field
+          tc_mma_f16(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc,
+                     (it | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+      }
+      tc_commit(tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;     // tile row
+    const int it_ = m / a.tF, if_ = m - it_ * a.tF;
+    const int t = t0 + it_, f = f0 + if_;
+    const bool row_ok = (t < a.To) && (f < a.Fo);
+    bool masked = false;
+    if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
+    const long long row = ((long long)b * a.To + t) * a.Fo + f;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+    const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (c0 >= ncols) break;  // warp-uniform
+      uint32_t r[16];
+      tc_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
+      tc_wait_ld();
+      if (!row_ok) continue;
+      const int co = n0 + c0;
+      const int nvalid = min(16, a.Cout - co);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      if (a.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
+      }
+      if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid,
+                                       (a.y_raw_vec >> 8) & 1);
+      if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid,
+                                       (a.y_raw_vec >> 9) & 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
+      if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid,
+                                      a.y_raw_vec & 1);
+      if (a.y_act != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+        store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, a.y_act_vec & 1);
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable (err %d)", (int)e);
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int pick_tile_n(int Cout) {
+  if (Cout <= 16) return 16;
+  if (Cout <= 32) return 32;
+  if (Cout <= 64) return 64;
+  if (Cout <= 128) return 128;
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  // minimise padding between 128- and 256-wide tiles, prefer the wider one on ties
+  int p256 = (Cout + 255) / 256 * 256, p128 = (Cout + 127) / 128 * 128;
+  return p128 < p256 ? 128 : 256;
+}
+
+template <int BN, int BK>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs& a, dim3 grid,
+                       cudaStream_t st) {
+  constexpr int STAGE_BYTES = 128 * BK * 2 + BN * BK * 2;
+  const int budget = (BN >= 256 ? 196 : 98) * 1024;
+  int stages = budget / STAGE_BYTES;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 2) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
+    attr_set = true;
+  }
+  conv_igemm_kernel<BN, BK><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
+static int esize(int dtype) { return dtype == AS_F32 ? 4 : 2; }
+static int vec_ok(const void* p, long long ld, int dtype) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((ld * esize(dtype)) & 15) == 0) ? 1 : 0;
+}
+
+}  // namespace asb
+
+extern "C" int32_t as_conv_tile_n(int32_t Cout) { return asb::pick_tile_n(Cout); }
+
+extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
+  using namespace asb;
+  ASB_REQUIRE(p != nullptr, AS_ERR_SHAPE, "as_conv_igemm: null params");
+  ASB_REQUIRE(p->x_dtype == AS_F16 || p->x_dtype == AS_BF16, AS_ERR_DTYPE,
+              "as_conv_igemm: x must be f16 or bf16");
+  ASB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0 && p->Cin > 0 && p->Cout > 0 && p->To > 0 && p->Fo > 0,
+              AS_ERR_SHAPE, "as_conv_igemm: non-positive dimension");
+  ASB_REQUIRE(p->ntaps >= 1 && p->ntaps <= CV_MAX_TAPS, AS_ERR_SHAPE,
+              "as_conv_igemm: ntaps=%d out of range [1,%d]", p->ntaps, CV_MAX_TAPS);
+  ASB_REQUIRE(p->x && p->w && p->tap_dt && p->tap_df, AS_ERR_SHAPE, "as_conv_igemm: null pointer");
+  const int bk = p->Cin >= 64 ? 64 : 32;
+  const int bn = pick_tile_n(p->Cout);
+  ASB_REQUIRE(p->CinP % bk == 0 && p->CinP >= p->Cin, AS_ERR_SHAPE,
+              "as_conv_igemm: CinP=%d must be a multiple of %d and >= Cin=%d", p->CinP, bk, p->Cin);
+  ASB_REQUIRE(p->CoutP % bn == 0 && p->CoutP >= p->Cout, AS_ERR_SHAPE,
+              "as_conv_igemm: CoutP=%d must be a multiple of %d and >= Cout=%d", p->CoutP, bn,
+              p->Cout);
+  ASB_REQUIRE((p->x_ld % 8) == 0 && p->x_ld >= p->Cin, AS_ERR_ALIGN,
+              "as_conv_igemm: x_ld=%lld must be a multiple of 8 and >= Cin", (long long)p->x_ld);
+  ASB_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
+              AS_ERR_ALIGN, "as_conv_igemm: x and w must be 16-byte aligned");
+  ASB_REQUIRE(p->y_raw || p->y_act, AS_ERR_SHAPE, "as_conv_igemm: no output requested");
+  ASB_REQUIRE(p->stats == nullptr, AS_ERR_SHAPE, "as_conv_igemm: fused stats not available yet");
+  int rc = check_arch();
+  if (rc != AS_OK) return rc;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return AS_ERR_CUDA;
+
+  // rows of a tile: tF = largest power of two dividing Fo (capped at 128), tT = 128 / tF, so the
+  // 128-row rectangle never straddles the F edge (F = 80/40/20/10/5 on this path, 1 for 1-D)
+  int tF = 1;
+  while (tF < 128 && (p->Fo % (tF * 2)) == 0) tF <<= 1;
+  const int tT = 128 / tF;
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = p->B; a.To = p->To; a.Fo = p->Fo; a.Cout = p->Cout; a.CoutP = p->CoutP;
+  a.tT = tT; a.tF = tF;
+  a.n_ttiles = (p->To + tT - 1) / tT;
+  a.n_ftiles = (p->Fo + tF - 1) / tF;
+  a.ntaps = p->ntaps; a.kchunks = p->CinP / bk;
+  for (int j = 0; j < p->ntaps; ++j) { a.tap_dt[j] = p->tap_dt[j]; a.tap_df[j] = p->tap_df[j]; }
+  const uint32_t fmt = (p->x_dtype == AS_BF16) ? 1u : 0u;
+  a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  a.bias = p->bias;
+  a.res1 = p->res1; a.res1_dtype = p->res1_dtype; a.res1_ld = p->res1_ld;
+  a.res2 = p->res2; a.res2_dtype = p->res2_dtype; a.res2_ld = p->res2_ld;
+  a.out_scale = p->out_scale;
+  a.y_raw = p->y_raw; a.y_raw_dtype = p->y_raw_dtype; a.y_raw_ld = p->y_raw_ld;
+  a.y_act = p->y_act; a.y_act_dtype = p->y_act_dtype; a.y_act_ld = p->y_act_ld;
+  a.y_raw_vec = (p->y_raw ? vec_ok(p->y_raw, p->y_raw_ld, p->y_raw_dtype) : 0) |
+                ((p->res1 ? vec_ok(p->res1, p->res1_ld, p->res1_dtype) : 0) << 8) |
+                ((p->res2 ? vec_ok(p->res2, p->res2_ld, p->res2_dtype) : 0) << 9);
+  a.y_act_vec = p->y_act ? vec_ok(p->y_act, p->y_act_ld, p->y_act_dtype) : 0;
+  a.act = p->act; a.slope = p->slope;
+  a.lens = p->lens;
+  a.stats = p->stats;
+
+  const CUtensorMapDataType dt =
+      p->x_dtype == AS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmA, tmW;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->F, (cuuint64_t)p->T, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->F,
+                             (cuuint64_t)p->x_ld * 2 * p->F * p->T};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)tF, (cuuint32_t)tT, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(p->x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p->CinP, (cuuint64_t)p->ntaps * p->CoutP};
+    cuuint64_t strides[1] = {(cuuint64_t)p->CinP * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmW, dt, 2, const_cast<void*>(p->w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+  }
+
+  dim3 grid((unsigned)(p->B * a.n_ttiles * a.n_ftiles), (unsigned)(p->CoutP / bn), 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define CV_CASE(BN_, BK_) \
+  if (bn == BN_ && bk == BK_) return launch_conv<BN_, BK_>(tmA, tmW, a, grid, st);
+  CV_CASE(16, 32) CV_CASE(32, 32) CV_CASE(64, 32) CV_CASE(128, 32) CV_CASE(256, 32)
+  CV_CASE(16, 64) CV_CASE(32, 64) CV_CASE(64, 64) CV_CASE(128, 64) CV_CASE(256, 64)
+#undef CV_CASE
+  set_error("as_conv_igemm: no kernel for tile_n=%d bk=%d", bn, bk);
+  return AS_ERR_SHAPE;
+}

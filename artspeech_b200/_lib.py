@@ -85,3 +85,27 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().as_last_error()
         raise AsError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+# ---- memory-bound / small kernels -----------------------------------------------------------
+_V, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SIGNATURES.update({
+    "as_embed": (C.c_int, [_V, _V, _I, _I, _I, _I, _F, _V, _V, _V, _I, _V]),
+    "as_layernorm": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _V, _F, _I, _F, _V, _V, _I, _L, _V, _I, _L, _V]),
+    "as_relpos_attention": (C.c_int, [_V, _L, _V, _V, _I, _I, _I, _I, _I, _V, _V, _I, _L, _V]),
+    "as_conformer_attention": (C.c_int, [_V, _V, _V, _L, _V, _V, _V, _I, _I, _I, _I, _V, _V, _I, _L, _V]),
+    "as_instnorm_stats": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _F, _V, _V]),
+    "as_adain_apply": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _V, _L, _F, _V, _V, _V, _V, _I, _L, _V]),
+    "as_repeat_rows": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _I, _L, _V]),
+    "as_length_regulate": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _V, _I, _I, _V, _I, _L, _V, _V]),
+    "as_conv_small": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _I, c_i32_p, c_i32_p, _I, _V,
+                                _V, _I, _L, _V, _I, _L, _I, _F, _V]),
+    "as_dwconv": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _I, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I,
+                            _V, _V, _I, _F, _V, _I, _L, _V]),
+    "as_avgpool": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _I, _I, _V, _I, _L, _V]),
+    "as_affine_act_maxpool": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _F, _I, _V, _I, _L, _V]),
+    "as_global_avgpool": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _I, _F, _V, _I, _L, _V]),
+    "as_bilstm": (C.c_int, [_V, _L, _V, _I, _I, _I, _V, _V, _I, _L, _V]),
+    "as_lstm_onestep": (C.c_int, [_V, _L, _L, _I, _V, _I, _L, _V]),
+    "as_log_norm": (C.c_int, [_V, _I, _I, _I, _V, _V]),
+    "as_transpose_cast": (C.c_int, [_V, _I, _V, _I, _I, _I, _I, _L, _I, _V, _V, _V, _V]),
+})

@@ -1,0 +1,300 @@
+// Attention kernels (fp32 on CUDA cores; attention is <3 % of the path's FLOPs).
+//   relpos_attention    — windowed relative-position MHA of RelTransformerEnc.py:138-169, fused:
+//                         QK^T + rel-key bias, length mask, softmax, PV + rel-value term.
+//   conformer_attention — Transformer-XL attention with the reference's view-based relative shift
+//                         (Utils/EMA/conformer/conformer/attention.py:72-113).
+// Neither materialises the [B,H,T,T] score tensor in HBM (the reference does, plus pad/view skew
+// copies); scores live in shared memory per query block.
+#include "common.cuh"
+
+namespace asb {
+
+// ---------------------------------------------------------------------------------------------
+// relpos attention.  CTA = 8 warps, each warp owns QW = 2 consecutive queries of one (b, h);
+// K / V tiles of 32 keys are staged in shared memory and shared by the CTA's 16 queries.
+// ---------------------------------------------------------------------------------------------
+constexpr int RA_WARPS = 8;
+constexpr int RA_QW = 2;
+constexpr int RA_QT = RA_WARPS * RA_QW;  // queries per CTA
+constexpr int RA_KT = 32;                // keys per tile
+constexpr int RA_MAXW = 9;               // 2*window+1 <= 9
+
+template <int D>
+__global__ void __launch_bounds__(RA_WARPS * 32)
+relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float* __restrict__ relk,
+                        const float* __restrict__ relv, int window, int T, int H,
+                        const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  extern __shared__ float sm[];
+  constexpr int KP = D + 1;                 // padded pitch: conflict-free row reads
+  float* kv = sm;                           // [RA_KT][KP]
+  float* qs = kv + RA_KT * KP;              // [RA_QT][D]
+  float* qe = qs + RA_QT * D;               // [RA_QT][RA_MAXW] q . E_k[r]
+  float* sc = qe + RA_QT * RA_MAXW;         // [RA_QT][Tpad] scores / probabilities
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * RA_QT;
+  const int len = lens ? min(lens[b], T) : T;
+  const int Tpad = (T + 31) & ~31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nrel = 2 * window + 1;
+  const float scale = rsqrtf((float)D);
+  const float* base = qkv + (long long)b * T * ld;
+  const int HD = H * D;
+
+  if (q0 >= len) {
+    // whole query block is padding: write zeros
+    for (int i = tid; i < RA_QT * D; i += blockDim.x) {
+      int qi = q0 + i / D, d = i % D;
+      if (qi < T) stany(out, ((long long)b * T + qi) * out_ld + h * D + d, 0.f, odt);
+    }
+    return;
+  }
+
+  // stage the CTA's queries
+  for (int i = tid; i < RA_QT * D; i += blockDim.x) {
+    int qi = q0 + i / D, d = i % D;
+    qs[i] = qi < T ? base[(long long)qi * ld + h * D + d] : 0.f;
+  }
+  __syncthreads();
+  // q . E_k[r]
+  for (int i = warp; i < RA_QT * RA_MAXW; i += RA_WARPS) {
+    int ql = i / RA_MAXW, r = i % RA_MAXW;
+    float s = 0.f;
+    if (r < nrel)
+      for (int d = lane; d < D; d += 32) s += qs[ql * D + d] * relk[r * D + d];
+    s = warp_sum(s);
+    if (lane == 0) qe[i] = s;
+  }
+  __syncthreads();
+
+  // ---- scores ----
+  const int ntiles = (len + RA_KT - 1) / RA_KT;
+  for (int kt = 0; kt < ntiles; ++kt) {
+    for (int i = tid; i < RA_KT * D; i += blockDim.x) {
+      int j = kt * RA_KT + i / D, d = i % D;
+      kv[(i / D) * KP + d] = j < len ? base[(long long)j * ld + HD + h * D + d] : 0.f;
+    }
+    __syncthreads();
+    const int j = kt * RA_KT + lane;
+    float s[RA_QW];
+#pragma unroll
+    for (int u = 0; u < RA_QW; ++u) s[u] = 0.f;
+    const float* kr = kv + lane * KP;
+    for (int d = 0; d < D; ++d) {
+      const float kd = kr[d];
+#pragma unroll
+      for (int u = 0; u < RA_QW; ++u) s[u] += qs[(warp * RA_QW + u) * D + d] * kd;
+    }
+#pragma unroll
+    for (int u = 0; u < RA_QW; ++u) {
+      const int ql = warp * RA_QW + u, qi = q0 + ql;
+      float v = s[u];
+      const int rel = j - qi;
+      if (rel >= -window && rel <= window) v += qe[ql * RA_MAXW + rel + window];
+      v *= scale;
+      if (j < Tpad) sc[ql * Tpad + j] = (j < len) ? v : -INFINITY;
+    }
+    __syncthreads();
+  }
+
+  // ---- softmax over keys < len (masked keys contribute exp(-1e4 - max) == 0 in fp32) ----
+#pragma unroll
+  for (int u = 0; u < RA_QW; ++u) {
+    const int ql = warp * RA_QW + u;
+    float* row = sc + ql * Tpad;
+    float m = -INFINITY;
+    for (int j = lane; j < len; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < len; j += 32) { float e = expf(row[j] - m); row[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < len; j += 32) row[j] *= inv;
+  }
+  __syncthreads();
+
+  // ---- P . V (+ relative values) ----
+  constexpr int DPL = D / 32;  // output dims per lane
+  float acc[RA_QW][DPL];
+#pragma unroll
+  for (int u = 0; u < RA_QW; ++u)
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) acc[u][c] = 0.f;
+  for (int kt = 0; kt < ntiles; ++kt) {
+    for (int i = tid; i < RA_KT * D; i += blockDim.x) {
+      int j = kt * RA_KT + i / D, d = i % D;
+      kv[(i / D) * KP + d] = j < len ? base[(long long)j * ld + 2 * HD + h * D + d] : 0.f;
+    }
+    __syncthreads();
+    const int jn = min(RA_KT, len - kt * RA_KT);
+    for (int jj = 0; jj < jn; ++jj) {
+      float p[RA_QW];
+#pragma unroll
+      for (int u = 0; u < RA_QW; ++u) p[u] = sc[(warp * RA_QW + u) * Tpad + kt * RA_KT + jj];
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) {
+        const float vv = kv[jj * KP + lane + 32 * c];
+#pragma unroll
+        for (int u = 0; u < RA_QW; ++u) acc[u][c] += p[u] * vv;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < RA_QW; ++u) {
+    const int ql = warp * RA_QW + u, qi = q0 + ql;
+    if (qi >= T) continue;
+    const bool valid = qi < len;
+    if (valid) {
+      for (int r = -window; r <= window; ++r) {
+        const int j = qi + r;
+        if (j < 0 || j >= len) continue;
+        const float p = sc[ql * Tpad + j];
+#pragma unroll
+        for (int c = 0; c < DPL; ++c) acc[u][c] += p * relv[(r + window) * D + lane + 32 * c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < DPL; ++c)
+      stany(out, ((long long)b * T + qi) * out_ld + h * D + lane + 32 * c, valid ? acc[u][c] : 0.f, odt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conformer attention: one warp per (b, h, query); K / pos / V rows are read straight from
+// global memory (L1/L2 resident: T*H*D*4 bytes per tensor).
+// ---------------------------------------------------------------------------------------------
+constexpr int CA_WARPS = 4;
+
+template <int D>
+__global__ void __launch_bounds__(CA_WARPS * 32)
+conformer_attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                           const float* __restrict__ v, long long ld, const float* __restrict__ pos,
+                           const float* __restrict__ ub, const float* __restrict__ vb, int T, int H,
+                           const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int a = blockIdx.x * CA_WARPS + warp;  // query
+  const int len = lens ? min(lens[b], T) : T;
+  const int Tpad = (T + 31) & ~31;
+  float* qu = sm + warp * (3 * D + Tpad);   // q_a + u
+  float* qv0 = qu + D;                      // q_a + v
+  float* qv1 = qv0 + D;                     // q_{a+1} + v
+  float* sc = qv1 + D;                      // [Tpad]
+  if (a >= T) return;
+  const int HD = H * D;
+  if (a >= len) {
+    for (int d = lane; d < D; d += 32) stany(out, ((long long)b * T + a) * out_ld + h * D + d, 0.f, odt);
+    return;
+  }
+  const float* qb = q + (long long)b * T * ld + h * D;
+  const float* kb = k + (long long)b * T * ld + h * D;
+  const float* vbase = v + (long long)b * T * ld + h * D;
+  for (int d = lane; d < D; d += 32) {
+    const float qa = qb[(long long)a * ld + d];
+    const float qn = (a + 1 < len) ? qb[(long long)(a + 1) * ld + d] : 0.f;
+    qu[d] = qa + ub[h * D + d];
+    qv0[d] = qa + vb[h * D + d];
+    qv1[d] = qn + vb[h * D + d];
+  }
+  __syncwarp();
+  const float inv_sqrt = rsqrtf((float)HD);
+  // the shift is defined on this item's own [len x len] score matrix
+  const int L = len;
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) {
+    const float* kr = kb + (long long)j * ld;
+    float s = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < D; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+      s += qu[d] * kk.x + qu[d + 1] * kk.y + qu[d + 2] * kk.z + qu[d + 3] * kk.w;
+    }
+    // relative shift (attention.py:105-113): flat index of out[a][j] in the padded tensor
+    const long long f = (long long)(a + 1) * L + j;
+    const int i2 = (int)(f / (L + 1)), jj = (int)(f % (L + 1));
+    if (jj != 0) {
+      const float* pr = pos + (long long)(jj - 1) * HD + h * D;
+      const float* qq = (i2 == a) ? qv0 : qv1;
+      float ps = 0.f;
+#pragma unroll 4
+      for (int d = 0; d < D; d += 4) {
+        const float4 pp = *reinterpret_cast<const float4*>(pr + d);
+        ps += qq[d] * pp.x + qq[d + 1] * pp.y + qq[d + 2] * pp.z + qq[d + 3] * pp.w;
+      }
+      s += ps;
+    }
+    s *= inv_sqrt;
+    sc[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) { float e = expf(sc[j] - m); sc[j] = e; sum += e; }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  __syncwarp();
+  constexpr int DPL = D / 32;
+  float acc[DPL];
+#pragma unroll
+  for (int c = 0; c < DPL; ++c) acc[c] = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float p = sc[j];
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) acc[c] += p * vbase[(long long)j * ld + lane + 32 * c];
+  }
+#pragma unroll
+  for (int c = 0; c < DPL; ++c)
+    stany(out, ((long long)b * T + a) * out_ld + h * D + lane + 32 * c, acc[c] * inv, odt);
+}
+
+}  // namespace asb
+
+using namespace asb;
+
+extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float* emb_rel_k,
+                                   const float* emb_rel_v, int32_t window, int32_t B, int32_t T,
+                                   int32_t H, int32_t D, const int32_t* lens, void* out,
+                                   int32_t out_dtype, int64_t out_ld, void* stream) {
+  if (B * T == 0) return AS_OK;
+  ASB_REQUIRE(qkv && emb_rel_k && emb_rel_v && out, AS_ERR_SHAPE, "as_relpos_attention: null pointer");
+  ASB_REQUIRE(D == 128, AS_ERR_SHAPE, "as_relpos_attention: head dim %d unsupported (128 only)", D);
+  ASB_REQUIRE(window >= 0 && 2 * window + 1 <= RA_MAXW, AS_ERR_SHAPE, "as_relpos_attention: window");
+  const int Tpad = (T + 31) & ~31;
+  const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 1) + RA_QT * D + RA_QT * RA_MAXW + (size_t)RA_QT * Tpad);
+  ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_relpos_attention: T=%d too long for the score buffer", T);
+  static bool attr = false;
+  if (!attr) {
+    ASB_CUDA(cudaFuncSetAttribute(relpos_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid((T + RA_QT - 1) / RA_QT, H, B);
+  relpos_attention_kernel<128><<<grid, RA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      qkv, qkv_ld, emb_rel_k, emb_rel_v, window, T, H, lens, out, out_dtype, out_ld);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
+extern "C" int as_conformer_attention(const float* q, const float* k, const float* v, int64_t qkv_ld,
+                                      const float* pos, const float* u_bias, const float* v_bias,
+                                      int32_t B, int32_t T, int32_t H, int32_t D,
+                                      const int32_t* lens, void* out, int32_t out_dtype,
+                                      int64_t out_ld, void* stream) {
+  if (B * T == 0) return AS_OK;
+  ASB_REQUIRE(q && k && v && pos && u_bias && v_bias && out, AS_ERR_SHAPE, "as_conformer_attention: null pointer");
+  ASB_REQUIRE(D == 64, AS_ERR_SHAPE, "as_conformer_attention: head dim %d unsupported (64 only)", D);
+  ASB_REQUIRE((qkv_ld % 4) == 0 && ((H * D) % 4) == 0, AS_ERR_ALIGN, "as_conformer_attention: ld must be a multiple of 4");
+  const int Tpad = (T + 31) & ~31;
+  const size_t smem = sizeof(float) * (size_t)CA_WARPS * (3 * D + Tpad);
+  ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_conformer_attention: T=%d too long", T);
+  static bool attr = false;
+  if (!attr) {
+    ASB_CUDA(cudaFuncSetAttribute(conformer_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid((T + CA_WARPS - 1) / CA_WARPS, H, B);
+  conformer_attention_kernel<64><<<grid, CA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}

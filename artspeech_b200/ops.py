@@ -195,3 +195,266 @@ def taps_1d(k: int, dilation: int = 1, padding: Optional[int] = None):
 def taps_2d(kt: int, kf: int, pad_t: int, pad_f: int):
     """Conv2d taps over (T, F); order matches ``w.permute`` in ``conv2d_weight_taps``."""
     return [(jt - pad_t, jf - pad_f) for jt in range(kt) for jf in range(kf)]
+
+
+# --------------------------------------------------------------------------------------------
+# memory-bound / small kernels
+# --------------------------------------------------------------------------------------------
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dims(x: torch.Tensor):
+    """(B, T, F, C) of a channels-last 3-D or 4-D tensor."""
+    if x.dim() == 3:
+        return x.shape[0], x.shape[1], 1, x.shape[2]
+    return tuple(x.shape)
+
+
+def _i32(t: Optional[torch.Tensor], name: str):
+    if t is not None and t.dtype != torch.int32:
+        raise _lib.AsError(f"{name}: lens must be int32")
+    return t
+
+
+def _run(name: str, x: torch.Tensor, *args):
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        rc = getattr(lib, name)(*args, _stream(x))
+    _lib.check(rc, name)
+    _count()
+
+
+def embed(tokens, table, scale, lens, *, out32: bool, out16=None):
+    """``tokens`` int64 [B,T]; returns (fp32 [B,T,C] or None, 16-bit [B,T,C] or None)."""
+    _require_cuda(tokens, "embed")
+    B, T = tokens.shape
+    C_ = table.shape[1]
+    o32 = torch.empty(B, T, C_, dtype=torch.float32, device=tokens.device) if out32 else None
+    o16 = torch.empty(B, T, C_, dtype=out16, device=tokens.device) if out16 is not None else None
+    _run("as_embed", tokens, tokens.contiguous().data_ptr(), table.data_ptr(), table.shape[0], B, T, C_,
+         float(scale), _p(_i32(lens, "embed")), _p(o32), _p(o16), dtype_code(out16) if out16 is not None else 0)
+    return o32, o16
+
+
+def layernorm(x, gamma, beta, eps, *, act=ACT_NONE, slope=0.0, lens=None, out_a=None, out_b=None):
+    """Row-wise LayerNorm over channels of ``x`` [B,T,C]; ``out_a``/``out_b``: dtype or tensor."""
+    _require_cuda(x, "layernorm")
+    B, T, C_ = x.shape
+    oa = _out_arg(out_a, (B, T, C_), x.device)
+    ob = _out_arg(out_b, (B, T, C_), x.device)
+    _run("as_layernorm", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "layernorm.x"), B, T, C_,
+         gamma.data_ptr(), beta.data_ptr(), float(eps), int(act), float(slope), _p(_i32(lens, "layernorm")),
+         _p(oa), dtype_code(oa.dtype) if oa is not None else 0, _rows_ld(oa, "ln.a") if oa is not None else 0,
+         _p(ob), dtype_code(ob.dtype) if ob is not None else 0, _rows_ld(ob, "ln.b") if ob is not None else 0)
+    return oa, ob
+
+
+def relpos_attention(qkv, emb_rel_k, emb_rel_v, window, n_heads, lens, out_dtype):
+    """``qkv`` fp32 [B,T,3*H*D] -> [B,T,H*D]."""
+    _require_cuda(qkv, "relpos_attention")
+    B, T, C3 = qkv.shape
+    HD = C3 // 3
+    out = torch.empty(B, T, HD, dtype=out_dtype, device=qkv.device)
+    _run("as_relpos_attention", qkv, qkv.data_ptr(), _rows_ld(qkv, "qkv"), emb_rel_k.data_ptr(),
+         emb_rel_v.data_ptr(), int(window), B, T, n_heads, HD // n_heads, _p(_i32(lens, "relpos")),
+         out.data_ptr(), dtype_code(out_dtype), HD)
+    return out
+
+
+def conformer_attention(q, k, v, pos, u_bias, v_bias, n_heads, lens, out_dtype):
+    """``q,k,v`` fp32 views [B,T,H*D] with a common row stride; ``pos`` fp32 [T,H*D]."""
+    _require_cuda(q, "conformer_attention")
+    B, T, HD = q.shape
+    ld = _rows_ld(q, "q")
+    assert _rows_ld(k, "k") == ld and _rows_ld(v, "v") == ld
+    out = torch.empty(B, T, HD, dtype=out_dtype, device=q.device)
+    _run("as_conformer_attention", q, q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, pos.data_ptr(),
+         u_bias.data_ptr(), v_bias.data_ptr(), B, T, n_heads, HD // n_heads, _p(_i32(lens, "conf")),
+         out.data_ptr(), dtype_code(out_dtype), HD)
+    return out
+
+
+def instnorm_stats(x, lens, eps=1e-5):
+    """``x`` [B,T,C] -> stats fp32 [B,C,2] = (mean, rstd) over valid frames."""
+    _require_cuda(x, "instnorm_stats")
+    B, T, C_ = x.shape
+    st = torch.empty(B, C_, 2, dtype=torch.float32, device=x.device)
+    _run("as_instnorm_stats", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "in.x"), B, T, C_,
+         _p(_i32(lens, "instnorm")), float(eps), st.data_ptr())
+    return st
+
+
+def adain_apply(x, stats, gb, slope, lens, out_dtype, up_w=None, up_b=None, out=None):
+    """AdaIN + LeakyReLU (+ depthwise ConvTranspose upsample).  ``gb`` fp32 view [B, 2C]."""
+    _require_cuda(x, "adain_apply")
+    B, T, C_ = x.shape
+    To = 2 * T if up_w is not None else T
+    if out is None:
+        out = torch.empty(B, To, C_, dtype=out_dtype, device=x.device)
+    assert gb.shape == (B, 2 * C_) and gb.stride(1) == 1
+    _run("as_adain_apply", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "adain.x"), B, T, C_,
+         stats.data_ptr(), gb.data_ptr(), gb.stride(0), float(slope), _p(_i32(lens, "adain")), _p(up_w),
+         _p(up_b), out.data_ptr(), dtype_code(out.dtype), _rows_ld(out, "adain.out"))
+    return out
+
+
+def repeat_rows(x, rep, lens, out_dtype=None, out=None):
+    _require_cuda(x, "repeat_rows")
+    B, T, C_ = x.shape
+    if out is None:
+        out = torch.empty(B, T * rep, C_, dtype=out_dtype or x.dtype, device=x.device)
+    _run("as_repeat_rows", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "rep.x"), B, T, C_, int(rep),
+         _p(_i32(lens, "repeat")), out.data_ptr(), dtype_code(out.dtype), _rows_ld(out, "rep.out"))
+    return out
+
+
+def length_regulate(x, dur, lens_t, rep, To, out=None, out_dtype=None):
+    """``x`` [B,Tt,C], ``dur`` int32 [B,Tt] -> (out [B,To,C], out_lens int32 [B])."""
+    _require_cuda(x, "length_regulate")
+    B, Tt, C_ = x.shape
+    if out is None:
+        out = torch.empty(B, To, C_, dtype=out_dtype or x.dtype, device=x.device)
+    olens = torch.empty(B, dtype=torch.int32, device=x.device)
+    assert dur.dtype == torch.int32 and dur.is_contiguous()
+    _run("as_length_regulate", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "lr.x"), B, Tt, C_,
+         dur.data_ptr(), _p(_i32(lens_t, "length_regulate")), int(rep), int(To), out.data_ptr(),
+         dtype_code(out.dtype), _rows_ld(out, "lr.out"), olens.data_ptr())
+    return out, olens
+
+
+@dataclass
+class SmallConv:
+    w: torch.Tensor            # fp32 [ntaps, Cout, Cin] device
+    bias: Optional[torch.Tensor]
+    taps: Sequence[tuple]
+    _dt: object = field(default=None, repr=False)
+    _df: object = field(default=None, repr=False)
+
+    def __post_init__(self):
+        n = len(self.taps)
+        self._dt = (C.c_int32 * n)(*[int(t[0]) for t in self.taps])
+        self._df = (C.c_int32 * n)(*[int(t[1]) for t in self.taps])
+
+
+def pack_small_conv(w_taps, bias, taps, device) -> SmallConv:
+    return SmallConv(w_taps.detach().float().contiguous().to(device),
+                     None if bias is None else bias.detach().float().contiguous().to(device), list(taps))
+
+
+def conv_small(x, sc: SmallConv, *, raw=None, act_out=None, act=ACT_NONE, slope=0.0, lens=None):
+    """Direct conv for Cin <= 16.  ``x`` [B,T,Cin] or [B,T,F,Cin]."""
+    _require_cuda(x, "conv_small")
+    B, T, F_, Cin = _dims(x)
+    ntaps, Cout, cin_w = sc.w.shape
+    assert cin_w == Cin
+    oshape = (B, T, Cout) if x.dim() == 3 else (B, T, F_, Cout)
+    r = _out_arg(raw, oshape, x.device)
+    a = _out_arg(act_out, oshape, x.device)
+    _run("as_conv_small", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "cs.x"), B, T, F_, Cin,
+         sc.w.data_ptr(), _p(sc.bias), ntaps, C.cast(sc._dt, _lib.c_i32_p), C.cast(sc._df, _lib.c_i32_p),
+         Cout, _p(_i32(lens, "conv_small")),
+         _p(r), dtype_code(r.dtype) if r is not None else 0, _rows_ld(r, "cs.raw") if r is not None else 0,
+         _p(a), dtype_code(a.dtype) if a is not None else 0, _rows_ld(a, "cs.act") if a is not None else 0,
+         int(act), float(slope))
+    return r, a
+
+
+def dwconv(x, w, bias, k, stride, pad, *, glu=False, act=ACT_NONE, slope=0.0, out_dtype=None,
+           lens_in=None, lens_out=None):
+    """Depthwise conv.  ``x`` [B,T,(F,)C(*2 if glu)]; ``w`` fp32 [kt*kf, C]; k/stride/pad = (t, f)."""
+    _require_cuda(x, "dwconv")
+    B, T, F_, Cx = _dims(x)
+    C_ = Cx // 2 if glu else Cx
+    (kt, kf), (st, sf), (pt, pf) = k, stride, pad
+    To = (T + 2 * pt - kt) // st + 1
+    Fo = (F_ + 2 * pf - kf) // sf + 1
+    oshape = (B, To, C_) if x.dim() == 3 else (B, To, Fo, C_)
+    out = torch.empty(oshape, dtype=out_dtype or x.dtype, device=x.device)
+    _run("as_dwconv", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "dw.x"), B, T, F_, C_, int(glu),
+         w.data_ptr(), _p(bias), kt, kf, st, sf, pt, pf, To, Fo, _p(_i32(lens_in, "dwconv")),
+         _p(_i32(lens_out, "dwconv")), int(act), float(slope), out.data_ptr(), dtype_code(out.dtype),
+         _rows_ld(out, "dw.out"))
+    return out
+
+
+def avgpool(x, pt, pf, out_dtype=None):
+    _require_cuda(x, "avgpool")
+    B, T, F_, C_ = _dims(x)
+    To, Fo = (T + pt - 1) // pt, F_ // pf
+    oshape = (B, To, C_) if x.dim() == 3 else (B, To, Fo, C_)
+    out = torch.empty(oshape, dtype=out_dtype or x.dtype, device=x.device)
+    _run("as_avgpool", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "ap.x"), B, T, F_, C_, pt, pf,
+         out.data_ptr(), dtype_code(out.dtype), _rows_ld(out, "ap.out"))
+    return out
+
+
+def affine_act_maxpool(x, scale, shift, slope, pf, out_dtype):
+    _require_cuda(x, "affine_act_maxpool")
+    B, T, F_, C_ = x.shape
+    out = torch.empty(B, T, F_ // pf, C_, dtype=out_dtype, device=x.device)
+    _run("as_affine_act_maxpool", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "mp.x"), B, T, F_, C_,
+         scale.data_ptr(), shift.data_ptr(), float(slope), int(pf), out.data_ptr(), dtype_code(out_dtype),
+         _rows_ld(out, "mp.out"))
+    return out
+
+
+def global_avgpool(x, slope, out_dtype, t_stride=1):
+    """LeakyReLU + mean over (T[::t_stride], F) -> [B, C]."""
+    _require_cuda(x, "global_avgpool")
+    B, T, F_, C_ = _dims(x)
+    out = torch.empty(B, C_, dtype=out_dtype, device=x.device)
+    _run("as_global_avgpool", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "gap.x"), B, T, F_, C_,
+         int(t_stride), float(slope), out.data_ptr(), dtype_code(out_dtype), C_)
+    return out
+
+
+def bilstm(xproj, whh_t, hidden, lens, out_dtype):
+    """``xproj`` fp32 [B,T,8H]; ``whh_t`` fp32 [2,H,4H] -> [B,T,2H]."""
+    _require_cuda(xproj, "bilstm")
+    B, T, _ = xproj.shape
+    out = torch.empty(B, T, 2 * hidden, dtype=out_dtype, device=xproj.device)
+    _run("as_bilstm", xproj, xproj.data_ptr(), _rows_ld(xproj, "lstm.x"), whh_t.data_ptr(), B, T, hidden,
+         _p(_i32(lens, "bilstm")), out.data_ptr(), dtype_code(out_dtype), 2 * hidden)
+    return out
+
+
+def lstm_onestep(xproj, hidden, out_dtype):
+    _require_cuda(xproj, "lstm_onestep")
+    B, T, _ = xproj.shape
+    out = torch.empty(B, T, 2 * hidden, dtype=out_dtype, device=xproj.device)
+    _run("as_lstm_onestep", xproj, xproj.data_ptr(), _rows_ld(xproj, "l1.x"), B * T, hidden, out.data_ptr(),
+         dtype_code(out_dtype), 2 * hidden)
+    return out
+
+
+def log_norm(mel):
+    """``mel`` fp32 [B,n_mels,T] (channels-first, contiguous) -> fp32 [B,T]."""
+    _require_cuda(mel, "log_norm")
+    mel = mel.contiguous()
+    B, M, T = mel.shape
+    out = torch.empty(B, T, dtype=torch.float32, device=mel.device)
+    _run("as_log_norm", mel, mel.data_ptr(), B, M, T, out.data_ptr())
+    return out
+
+
+def to_channels_last(src, out_dtype, lens=None, sub=None, mul=None, out=None):
+    """``src`` [B,C,T] contiguous -> [B,T,C] (``out`` may be a channel-slice view)."""
+    _require_cuda(src, "to_channels_last")
+    src = src.contiguous()
+    B, C_, T = src.shape
+    if out is None:
+        out = torch.empty(B, T, C_, dtype=out_dtype, device=src.device)
+    _run("as_transpose_cast", src, src.data_ptr(), dtype_code(src.dtype), out.data_ptr(), dtype_code(out.dtype),
+         B, C_, T, _rows_ld(out, "tcl.out"), 1, _p(sub), _p(mul), _p(_i32(lens, "to_cl")))
+    return out
+
+
+def to_channels_first(src, out_dtype, lens=None, sub=None, mul=None):
+    """``src`` [B,T,C] (view allowed) -> contiguous [B,C,T]."""
+    _require_cuda(src, "to_channels_first")
+    B, T, C_ = src.shape
+    out = torch.empty(B, C_, T, dtype=out_dtype, device=src.device)
+    _run("as_transpose_cast", src, src.data_ptr(), dtype_code(src.dtype), out.data_ptr(), dtype_code(out_dtype),
+         B, C_, T, _rows_ld(src, "tcf.src"), 0, _p(sub), _p(mul), _p(_i32(lens, "to_cf")))
+    return out

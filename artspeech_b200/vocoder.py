@@ -163,6 +163,9 @@ class Generator(nn.Module):
     def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``x``: mel ``[B, num_mels, T]`` -> waveform ``[B, 1, T*prod(upsample_rates)]`` (fp32)."""
         mel_cl = x.detach().transpose(1, 2).to(self.compute_dtype).contiguous()   # [B, T, 80]
+        if lengths is not None:  # frames beyond an utterance's length must not leak into it
+            keep = torch.arange(mel_cl.shape[1], device=mel_cl.device)[None, :] < lengths.to(mel_cl.device)[:, None]
+            mel_cl = mel_cl * keep.unsqueeze(-1).to(mel_cl.dtype)
         wav = self.forward_channels_last(mel_cl, lengths)
         return wav.view(wav.shape[0], 1, -1)
 

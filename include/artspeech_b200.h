@@ -115,6 +115,136 @@ typedef struct as_conv_params {
 int32_t as_conv_tile_n(int32_t Cout);
 int as_conv_igemm(const as_conv_params* p, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Memory-bound / small kernels.  Unless stated otherwise `x` may be any as_dtype and is addressed
+ * as rows of `*_ld` elements (channels-last, outer dims dense); `lens` (int32 [B], may be NULL)
+ * gives the valid number of T positions per batch item and rows beyond it are written as zeros.
+ * ------------------------------------------------------------------------------------------ */
+
+/* emb(x) * scale (Utils/RelTransformerEnc.py:372-373); out32 fp32 and/or out16 (16-bit) [B,T,C] */
+int as_embed(const int64_t* tokens, const float* table, int32_t n_vocab, int32_t B, int32_t T,
+             int32_t C, float scale, const int32_t* lens, float* out32, void* out16,
+             int32_t out16_dtype, void* stream);
+
+/* LayerNorm over the channel axis of channels-last rows: custom LN (RelTransformerEnc.py:272-290,
+ * eps 1e-4) and nn.LayerNorm (conformer, eps 1e-5).  y = act((x-mean)*rsqrt(var+eps)*gamma+beta).
+ * rows = B*T; up to two outputs (e.g. fp32 + 16-bit operand). */
+int as_layernorm(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t C,
+                 const float* gamma, const float* beta, float eps, int32_t act, float slope,
+                 const int32_t* lens, void* out_a, int32_t out_a_dtype, int64_t out_a_ld,
+                 void* out_b, int32_t out_b_dtype, int64_t out_b_ld, void* stream);
+
+/* Windowed relative-position multi-head self-attention (RelTransformerEnc.py:138-169, window 4,
+ * E_k/E_v [2w+1, D] shared by the heads).  qkv fp32 [B,T,3*H*D] (q | k | v), keys >= lens[b] get
+ * score -1e4 exactly like masked_fill; out [B,T,H*D]. */
+int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float* emb_rel_k,
+                        const float* emb_rel_v, int32_t window, int32_t B, int32_t T, int32_t H,
+                        int32_t D, const int32_t* lens, void* out, int32_t out_dtype,
+                        int64_t out_ld, void* stream);
+
+/* Conformer (Transformer-XL style) attention with the reference's view-based relative shift
+ * (Utils/EMA/conformer/conformer/attention.py:72-113): score = ((q+u).k + shift((q+v).p)) /
+ * sqrt(H*D); softmax over the valid keys of each item; . V.  q,k,v fp32 [B,T,H*D] rows of ld;
+ * pos fp32 [T, H*D] = pos_proj(PE[0:T]); the shift uses each item's own length. */
+int as_conformer_attention(const float* q, const float* k, const float* v, int64_t qkv_ld,
+                           const float* pos, const float* u_bias, const float* v_bias, int32_t B,
+                           int32_t T, int32_t H, int32_t D, const int32_t* lens, void* out,
+                           int32_t out_dtype, int64_t out_ld, void* stream);
+
+/* InstanceNorm1d statistics (models.py:230-240): stats[b][c] = {mean, rsqrt(biased var + eps)}
+ * over t < lens[b]. */
+int as_instnorm_stats(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T,
+                      int32_t C, const int32_t* lens, float eps, float* stats, void* stream);
+
+/* AdaIN + LeakyReLU (+ optional depthwise ConvTranspose1d k3 s2 "pool", models.py:172,189-192):
+ *   a[b,t,c] = lrelu(((x-mean)*rstd) * (1 + gamma[b,c]) + beta[b,c]),  gamma = gb[b*gb_ld + c],
+ *   beta = gb[b*gb_ld + C + c];  up_w == NULL: out[b,t] = a[b,t];
+ *   else out[b,2m] = a[m]*w[c][1] + up_b[c], out[b,2m+1] = a[m]*w[c][2] + a[m+1]*w[c][0] + up_b[c]
+ *   (a[len] = 0), out has 2T rows and is masked with 2*lens. */
+int as_adain_apply(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t C,
+                   const float* stats, const float* gb, int64_t gb_ld, float slope,
+                   const int32_t* lens, const float* up_w, const float* up_b, void* out,
+                   int32_t out_dtype, int64_t out_ld, void* stream);
+
+/* out[b, r, :] = x[b, r / rep, :] for r < rep*lens[b] else 0 (nearest upsample, models.py:261-270) */
+int as_repeat_rows(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t C,
+                   int32_t rep, const int32_t* lens, void* out, int32_t out_dtype, int64_t out_ld,
+                   void* stream);
+
+/* Length regulation (models.py:361-368 one-hot matmul == gather) fused with the decoder's x2
+ * nearest upsample (models.py:500): frame r of item b copies token j where
+ * cum[j] <= r / rep < cum[j+1], cum = exclusive prefix sum of dur[b, :lens_t[b]].
+ * x [B,Tt,C]; dur int32 [B,Tt]; out [B,To,C] (rows >= rep*sum(dur) zero); out_lens[b] = rep*sum. */
+int as_length_regulate(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t Tt,
+                       int32_t C, const int32_t* dur, const int32_t* lens_t, int32_t rep,
+                       int32_t To, void* out, int32_t out_dtype, int64_t out_ld,
+                       int32_t* out_lens, void* stream);
+
+/* Direct convolution for tiny input-channel counts (Cin <= 16) on CUDA cores: first layers of the
+ * 2-D stacks (1 -> 64, 3x3), F0/N/EMA 1x1 convs of the decoder (models.py:480-482, 502-504).
+ * x [B,T,F,Cin]; w fp32 [ntaps][Cout][Cin]; taps host arrays; stride 1; zero padding; outputs as
+ * as_conv_igemm (raw / activated). */
+int as_conv_small(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t F,
+                  int32_t Cin, const float* w, const float* bias, int32_t ntaps,
+                  const int32_t* tap_dt, const int32_t* tap_df, int32_t Cout, const int32_t* lens,
+                  void* y_raw, int32_t y_raw_dtype, int64_t y_raw_ld, void* y_act,
+                  int32_t y_act_dtype, int64_t y_act_ld, int32_t act, float slope, void* stream);
+
+/* Depthwise convolution over (T,F) with stride (models.py:27-31,116; conformer
+ * convolution.py:136-149 with glu != 0: the input has 2C channels and value = x[c]*sigmoid(x[C+c])).
+ * w fp32 [kt*kf][C] (BatchNorm already folded), bias [C] or NULL; out = act(conv). */
+int as_dwconv(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t F,
+              int32_t C, int32_t glu, const float* w, const float* bias, int32_t kt, int32_t kf,
+              int32_t st, int32_t sf, int32_t pt, int32_t pf, int32_t To, int32_t Fo,
+              const int32_t* lens_in, const int32_t* lens_out, int32_t act, float slope,
+              void* out, int32_t out_dtype, int64_t out_ld, void* stream);
+
+/* Average pooling pt x pf (stride = window) with the reference's replicate padding of the last T
+ * position when T is odd (models.py:43-57,127-130); To = ceil(T/pt), Fo = F/pf. */
+int as_avgpool(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t F,
+               int32_t C, int32_t pt, int32_t pf, void* out, int32_t out_dtype, int64_t out_ld,
+               void* stream);
+
+/* y = maxpool_F(lrelu(x*scale[c] + shift[c]), pf)  (Utils/JDC/model.py:163-167,34-38);
+ * Fo = F / pf (floor). */
+int as_affine_act_maxpool(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T,
+                          int32_t F, int32_t C, const float* scale, const float* shift,
+                          float slope, int32_t pf, void* out, int32_t out_dtype, int64_t out_ld,
+                          void* stream);
+
+/* out[b,c] = mean over (t in {0, ts, 2ts, ..} < T, f < F) of lrelu(x[b,t,f,c])
+ * (LeakyReLU + AdaptiveAvgPool, models.py:390-393; ts = 2 evaluates a stride-2 conv) */
+int as_global_avgpool(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T,
+                      int32_t F, int32_t C, int32_t t_stride, float slope, void* out,
+                      int32_t out_dtype, int64_t out_ld, void* stream);
+
+/* Bidirectional single-layer LSTM recurrence with packed-sequence semantics (PyTorch gate order
+ * i,f,g,o; models.py:555-564,606-618; Utils/JDC/model.py:128).  xproj fp32 [B,T,2*4H] =
+ * W_ih x + b_ih + b_hh for (forward | reverse); whh_t fp32 [2][H][4H] = weight_hh transposed
+ * (k-major, so the 4H gate threads read consecutive floats); out [B,T,2H] with (forward |
+ * reverse) halves, zeros beyond lens[b]; the reverse direction starts at lens[b]-1. */
+int as_bilstm(const float* xproj, int64_t xproj_ld, const float* whh_t, int32_t B, int32_t T,
+              int32_t H, const int32_t* lens, void* out, int32_t out_dtype, int64_t out_ld,
+              void* stream);
+
+/* One LSTM step from zero state per row (the reference's mis-oriented EMA LSTM at batch 1,
+ * Utils/EMA/EMA_Predictor.py:44,80): c = sig(i)*tanh(g), h = sig(o)*tanh(c) for both directions.
+ * xproj fp32 [rows, 2*4H] -> out [rows, 2H]. */
+int as_lstm_onestep(const float* xproj, int64_t xproj_ld, int64_t rows, int32_t H, void* out,
+                    int32_t out_dtype, int64_t out_ld, void* stream);
+
+/* log-norm energy (models.py:655-660): out[b,t] = log(||exp(mel[b,:,t]*4 - 4)||_2), mel fp32
+ * channels-first [B,n_mels,T] (the reference's own input layout). */
+int as_log_norm(const float* mel, int32_t B, int32_t n_mels, int32_t T, float* out, void* stream);
+
+/* Layout/dtype change between the reference's channels-first tensors and channels-last
+ * activations: dst[b,t,c] = src[b,c,t] (to_channels_last != 0, rows >= lens zeroed) or the
+ * inverse.  Optional per-channel affine y = (x - sub[c]) * mul[c] on the way. */
+int as_transpose_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int32_t B,
+                      int32_t C, int32_t T, int64_t cl_ld, int32_t to_channels_last,
+                      const float* sub, const float* mul, const int32_t* lens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

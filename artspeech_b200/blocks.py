@@ -95,22 +95,34 @@ class StyleFC:
         return [out[:, o:o + n] for o, n in plan["offs"]]
 
 
-def run_adain_block(p, x16, gb1, gb2, lens, dt, out=None, mid_dtype=torch.float32):
-    """AdainResBlk1d.forward (models.py:183-202) on channels-last ``x16`` [B, T, Cin].
+def run_adain_block(p, x, gb1, gb2, lens, dt, out=None, out16=None, x16=None, res_dtype=None,
+                    mid_dtype=torch.float32):
+    """AdainResBlk1d.forward (models.py:183-202) on channels-last ``x`` [B, T, Cin].
 
-    Returns (out [B, T', Cout] in ``dt`` (or written into ``out``), lens').  T' = 2T for upsample."""
-    st1 = ops.instnorm_stats(x16, lens)
-    a1 = ops.adain_apply(x16, st1, gb1, LRELU, lens, dt, p["up_w"], p["up_b"])
+    ``x`` is the residual stream (fp32 or 16-bit): it feeds the InstanceNorm statistics, AdaIN and the
+    identity shortcut.  A learned (1x1) shortcut needs a 16-bit GEMM operand: ``x16`` (defaults to
+    ``x`` when that already is 16-bit).  The result is written as ``res_dtype`` (default ``dt``) into
+    ``out`` (or a new tensor) and, when ``out16`` is given (dtype or view), additionally as a 16-bit
+    copy for the next block's 1x1 shortcut.  Returns (out, out16, lens'); T' = 2T for upsample."""
+    st1 = ops.instnorm_stats(x, lens)
+    a1 = ops.adain_apply(x, st1, gb1, LRELU, lens, dt, p["up_w"], p["up_b"])
     up = p["up_w"] is not None
     lens2 = lens * 2 if (up and lens is not None) else lens
     c1, _ = ops.conv(a1, p["conv1"], raw=mid_dtype, lens=lens2)
     st2 = ops.instnorm_stats(c1, lens2)
     a2 = ops.adain_apply(c1, st2, gb2, LRELU, lens2, dt)
-    xs = ops.repeat_rows(x16, 2, lens, dt) if up else x16           # shortcut: nearest x2 (models.py:261-270)
     if p["sc"] is not None:
+        xs = x16 if x16 is not None else x
+        if xs.dtype != dt:
+            raise ValueError("run_adain_block: a learned shortcut needs the 16-bit copy of x (x16=)")
+        if up:
+            xs = ops.repeat_rows(xs, 2, lens, dt)
         xs, _ = ops.conv(xs, p["sc"], raw=torch.float32)
-    res, _ = ops.conv(a2, p["conv2"], res1=xs, scale=INV_SQRT2, raw=(dt if out is None else out), lens=lens2)
-    return res, lens2
+    else:
+        xs = ops.repeat_rows(x, 2, lens) if up else x               # nearest x2 (models.py:261-270)
+    raw_spec = out if out is not None else (res_dtype or dt)
+    res, res16 = ops.conv(a2, p["conv2"], res1=xs, scale=INV_SQRT2, raw=raw_spec, act_out=out16, lens=lens2)
+    return res, res16, lens2
 
 
 # --------------------------------------------------------------------------------------------

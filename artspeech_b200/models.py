@@ -210,6 +210,7 @@ class DurationPredictor(nn_util.PlanMixin, nn.Module):
         self.dur_linear = nn.Linear(2 * d, style_dim // 4)
         self.d_hid, self.style_dim = d_hid, style_dim
         self.compute_dtype = torch.float16
+        self.res_dtype = torch.float32     # residual stream between AdaIN blocks
         self._init_plan()
 
     def _fc(self):
@@ -255,9 +256,14 @@ class DurationPredictor(nn_util.PlanMixin, nn.Module):
             else:
                 dstyle[idx] = ds.view(len(idx), -1)
         gbs = StyleFC.run(p["fc"], dstyle.contiguous())
-        _, x16 = self.text_encoder(texts, text_lengths, want_16bit=True)
+        x, _ = self.text_encoder(texts, text_lengths, want_16bit=False), None
+        rd = self.res_dtype
         for i, bp in enumerate(p["blocks"]):
-            x16, _ = run_adain_block(bp, x16, gbs[2 * i], gbs[2 * i + 1], lens, dt)
+            last = i == len(p["blocks"]) - 1
+            x, x16, _ = run_adain_block(bp, x, gbs[2 * i], gbs[2 * i + 1], lens, dt, res_dtype=rd,
+                                        out16=dt if (last and rd != dt) else None)
+        if x16 is None:
+            x16 = x
         xproj, _ = ops.conv(x16, p["lstm_proj"], raw=torch.float32)
         h16 = ops.bilstm(xproj, p["whh_t"], self.d_hid // 2, lens, dt)
         dur, _ = ops.conv(h16, p["out"], raw=torch.float32)                   # padded rows = bias, as in :562-565
@@ -286,6 +292,7 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
         self.EMA_proj = nn.Conv1d(h2, 10, 1, 1, 0)
         self.style_dim, self.d_hid = style_dim, d_hid
         self.compute_dtype = torch.float16
+        self.res_dtype = torch.float32     # residual stream between AdaIN blocks
         self._init_plan()
 
     # style slices of the 512-d style vector (models.py:597-599)
@@ -314,22 +321,29 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
 
     @torch.no_grad()
     def forward_cl(self, a16: torch.Tensor, style16: torch.Tensor, lens):
-        """``a16`` [B,L,512] 16-bit (length-regulated arts-encoder output), ``style16`` [B,512] ->
+        """``a16`` [B,L,512] (length-regulated arts-encoder output, ``res_dtype``), ``style16`` [B,512] ->
         (F0 [B,2L,1], N [B,2L,1], EMA [B,2L,10]) fp32 channels-last, lens*2."""
         p = self.plan(a16.device)
         dt = self.compute_dtype
+        if style16.dtype != dt:                         # only when a caller mixes compute dtypes
+            style16 = style16.to(dt)
         gbs = StyleFC.run(p["fc"], style16)
-        x16, _ = run_adain_block(p["shared"], a16, gbs[0], gbs[1], lens, dt)
+        rd = self.res_dtype
+        need16 = rd != dt
+        xs, _, _ = run_adain_block(p["shared"], a16, gbs[0], gbs[1], lens, dt, res_dtype=rd)
         outs = []
         g = 2
         lens2 = lens
         for name in ("F0", "N", "EMA"):
             bp = p["br"][name]
-            y, l = x16, lens
+            y, y16, l = xs, None, lens
             for j, blk in enumerate(bp["blocks"]):
-                y, l = run_adain_block(blk, y, gbs[g + 2 * j], gbs[g + 2 * j + 1], l, dt)
+                # blocks 1, 2 have a learned 1x1 shortcut (512->256->128): they need a 16-bit copy of
+                # their input; the last block's 16-bit copy is the LSTM projection's operand
+                y, y16, l = run_adain_block(blk, y, gbs[g + 2 * j], gbs[g + 2 * j + 1], l, dt, res_dtype=rd,
+                                            x16=y16, out16=dt if need16 else None)
             g += 6
-            xproj, _ = ops.conv(y, bp["lstm_proj"], raw=torch.float32)
+            xproj, _ = ops.conv(y16 if need16 else y, bp["lstm_proj"], raw=torch.float32)
             h16 = ops.bilstm(xproj, bp["whh_t"], self.d_hid // 4, l, dt)
             o, _ = ops.conv(h16, bp["out"], raw=torch.float32, lens=l)
             outs.append(o)
@@ -341,8 +355,8 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
         """Reference signature (models.py:596-621): ``A_ens`` [B,512,L], ``style`` [B,512] ->
         (F0 [B,1,2L], N [B,1,2L], EMA [B,10,2L])."""
         dt = self.compute_dtype
-        a16 = ops.to_channels_last(A_ens.detach().float(), dt)
-        f0, n, ema, _ = self.forward_cl(a16, style.detach().to(dt).contiguous(), None)
+        a_cl = ops.to_channels_last(A_ens.detach().float(), self.res_dtype)
+        f0, n, ema, _ = self.forward_cl(a_cl, style.detach().to(dt).contiguous(), None)
         cf = lambda t: ops.to_channels_first(t, torch.float32)
         return cf(f0), cf(n), cf(ema)
 
@@ -367,6 +381,7 @@ class Decoder(nn_util.PlanMixin, nn.Module):
                                      AdainResBlk1d(dec_dim, dec_dim, style_dim)])
         self.to_out = nn.Sequential(weight_norm(nn.Conv1d(dec_dim, dim_out, 1, 1, 0)))
         self.compute_dtype = torch.float16
+        self.res_dtype = torch.float32     # residual stream between AdaIN blocks (fp16 misses the mel tolerance)
         self._init_plan()
 
     def _fc(self):
@@ -387,32 +402,59 @@ class Decoder(nn_util.PlanMixin, nn.Module):
                     asr_res=nn_util.pack_conv1d(self.asr_res[0], dt, device),
                     to_out=nn_util.pack_conv1d(self.to_out[0], dt, device))
 
+    def alloc_inputs(self, B, Tm, device):
+        """(cat_res, cat16): the decoder's first concat buffer [B,Tm,640] in the residual-stream dtype
+        and in the compute dtype (the same tensor when both dtypes agree).  The caller fills channels
+        [0, 512) of both with the x2-upsampled, length-regulated text encoding."""
+        W = self.dec_dim + 128
+        cat16 = torch.empty(B, Tm, W, dtype=self.compute_dtype, device=device)
+        if self.res_dtype == self.compute_dtype:
+            return cat16, cat16
+        return torch.empty(B, Tm, W, dtype=self.res_dtype, device=device), cat16
+
     @torch.no_grad()
-    def forward_cl(self, cat0: torch.Tensor, style16, f0_cl, n_cl, ema_cl, lens):
-        """``cat0`` [B,Tm,640] 16-bit whose first 512 channels already hold the x2-upsampled
-        length-regulated text encoding; F0/N/EMA fp32 channels-last [B,Tm,{1,1,10}].
-        Returns mel fp32 [B,Tm,80] (zeros beyond ``lens``)."""
-        p = self.plan(cat0.device)
+    def forward_cl(self, cat_res: torch.Tensor, cat16: torch.Tensor, style16, f0_cl, n_cl, ema_cl, lens):
+        """``cat_res`` / ``cat16`` from ``alloc_inputs`` with channels [0,512) filled; F0/N/EMA fp32
+        channels-last [B,Tm,{1,1,10}].  Returns mel fp32 [B,Tm,80] (zeros beyond ``lens``).
+
+        Everything that feeds an InstanceNorm stays in ``res_dtype`` (fp32 by default): several
+        concat channels (bias-dominated F0/N/EMA features) have |mean| >> std, so a 16-bit copy of
+        the *pre-norm* value would lose the signal the norm then amplifies.  16-bit copies exist
+        only as GEMM operands (1x1 shortcuts, asr_res)."""
+        p = self.plan(cat16.device)
         dt = self.compute_dtype
-        B, Tm, _ = cat0.shape
+        if cat16.dtype != dt or style16.dtype != dt:     # only when a caller mixes compute dtypes
+            cat16, style16 = cat16.to(dt), style16.to(dt)
+        B, Tm, _ = cat16.shape
         D, bd, R = self.dec_dim, self.bottleneck_dim, self.residual_dim
-        big = torch.empty(B, Tm, bd + R + 128, dtype=dt, device=cat0.device)   # [x | asr_res | F0 | N | EMA]
-        for buf, base in ((cat0, D), (big, bd + R)):                           # concat fused: write slices
-            ops.conv_small(f0_cl, p["f0"], raw=buf[..., base:base + 32], lens=lens)
-            ops.conv_small(n_cl, p["n"], raw=buf[..., base + 32:base + 64], lens=lens)
-            ops.conv_small(ema_cl, p["ema"], raw=buf[..., base + 64:base + 128], lens=lens)
-        ops.conv(cat0[..., :D], p["asr_res"], raw=big[..., bd:bd + R], lens=lens)
+        rd = self.res_dtype
+        need16 = cat_res.dtype != dt
+        W = bd + R + 128
+        big16 = torch.empty(B, Tm, W, dtype=dt, device=cat16.device)             # [x | asr_res | F0 | N | EMA]
+        big = torch.empty(B, Tm, W, dtype=rd, device=cat16.device) if need16 else big16
+        for (buf, buf16), base in (((cat_res, cat16), D), ((big, big16), bd + R)):   # concat fused: write slices
+            for src, key, lo, hi in ((f0_cl, "f0", 0, 32), (n_cl, "n", 32, 64), (ema_cl, "ema", 64, 128)):
+                ops.conv_small(src, p[key], raw=buf[..., base + lo:base + hi],
+                               act_out=buf16[..., base + lo:base + hi] if need16 else None, lens=lens)
+        ops.conv(cat16[..., :D], p["asr_res"], raw=big[..., bd:bd + R],
+                 act_out=big16[..., bd:bd + R] if need16 else None, lens=lens)
         gbs = StyleFC.run(p["fc"], style16)
-        run_adain_block(p["encode"], cat0, gbs[0], gbs[1], lens, dt, out=big[..., :bd])
-        x = None
+        run_adain_block(p["encode"], cat_res, gbs[0], gbs[1], lens, dt, x16=cat16, out=big[..., :bd],
+                        out16=big16[..., :bd] if need16 else None)
+        x = x16 = None
         for i, bp in enumerate(p["decode"]):
             g1, g2 = gbs[2 + 2 * i], gbs[3 + 2 * i]
             if i < 2:
-                run_adain_block(bp, big, g1, g2, lens, dt, out=big[..., :bd])
+                run_adain_block(bp, big, g1, g2, lens, dt, x16=big16, out=big[..., :bd],
+                                out16=big16[..., :bd] if need16 else None)
             elif i == 2:
-                x, _ = run_adain_block(bp, big, g1, g2, lens, dt)
+                x, _, _ = run_adain_block(bp, big, g1, g2, lens, dt, x16=big16, res_dtype=rd)
             else:
-                x, _ = run_adain_block(bp, x, g1, g2, lens, dt)
+                last = i == len(p["decode"]) - 1
+                x, x16, _ = run_adain_block(bp, x, g1, g2, lens, dt, res_dtype=rd,
+                                            out16=dt if (last and need16) else None)
+        if need16:
+            x = x16
         mel, _ = ops.conv(x, p["to_out"], raw=torch.float32, lens=lens)
         return mel
 
@@ -422,11 +464,13 @@ class Decoder(nn_util.PlanMixin, nn.Module):
         F0/N [B,1,2L], EMA [B,10,2L] -> mel [B,80,2L]."""
         dt = self.compute_dtype
         B, D, L = asr.shape
-        cat0 = torch.empty(B, 2 * L, D + 128, dtype=dt, device=asr.device)
-        a16 = ops.to_channels_last(asr.detach().float(), dt)
-        ops.repeat_rows(a16, 2, None, out=cat0[..., :D])                       # F.interpolate(..., 2, 'nearest')
+        cat_res, cat16 = self.alloc_inputs(B, 2 * L, asr.device)
+        a_cl = ops.to_channels_last(asr.detach().float(), torch.float32)
+        ops.repeat_rows(a_cl, 2, None, out=cat_res[..., :D])                   # F.interpolate(..., 2, 'nearest')
+        if cat16 is not cat_res:
+            ops.repeat_rows(a_cl, 2, None, out=cat16[..., :D])
         cl = lambda t: ops.to_channels_last(t.detach().float(), torch.float32)
-        mel = self.forward_cl(cat0, Style.detach().to(dt).contiguous(), cl(F0), cl(N), cl(EMA), None)
+        mel = self.forward_cl(cat_res, cat16, Style.detach().to(dt).contiguous(), cl(F0), cl(N), cl(EMA), None)
         return ops.to_channels_first(mel, torch.float32)
 
 
@@ -489,11 +533,14 @@ class ArtsSpeech(nn.Module):
         style16 = style.to(dt).contiguous()
         # length regulation as a gather (the reference multiplies by a one-hot matrix, :362-368);
         # the decoder's nearest x2 upsample (:500) is fused into the same pass.
-        a16, lens_l = ops.length_regulate(A_en, dur, lens_t, 1, Lmax, out_dtype=dt)
-        cat0 = torch.empty(B, Tm, self.decoder.dec_dim + 128, dtype=dt, device=dev)
-        _, lens_m = ops.length_regulate(T_en, dur, lens_t, 2, Tm, out=cat0[..., :self.decoder.dec_dim])
-        f0, n, ema, _ = self.artsPredictor.forward_cl(a16, style16, lens_l)              # (:369)
-        mel_cl = self.decoder.forward_cl(cat0, style16, f0, n, ema, lens_m)              # (:370)
+        D = self.decoder.dec_dim
+        a_reg, lens_l = ops.length_regulate(A_en, dur, lens_t, 1, Lmax, out_dtype=self.artsPredictor.res_dtype)
+        cat_res, cat16 = self.decoder.alloc_inputs(B, Tm, dev)
+        _, lens_m = ops.length_regulate(T_en, dur, lens_t, 2, Tm, out=cat_res[..., :D])
+        if cat16 is not cat_res:
+            ops.length_regulate(T_en, dur, lens_t, 2, Tm, out=cat16[..., :D])
+        f0, n, ema, _ = self.artsPredictor.forward_cl(a_reg, style16, lens_l)            # (:369)
+        mel_cl = self.decoder.forward_cl(cat_res, cat16, style16, f0, n, ema, lens_m)    # (:370)
         mel = ops.to_channels_first(mel_cl, torch.float32)                               # [B,80,Tm]
         if return_aux:
             return mel, dict(mel_lengths=lens_m, pred_dur=pred_dur, duration=duration, style=style, T_en=T_en,

@@ -68,9 +68,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.isfile(path):
+    if not os.path.isfile(path) or not _build.is_current():
         if not build_if_missing:
-            raise AsError(f"{path} not built; run `python -m artspeech_b200.build`")
+            raise AsError(f"{path} missing or stale; run `python -m artspeech_b200.build`")
         _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():

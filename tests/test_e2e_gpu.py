@@ -1,0 +1,152 @@
+"""GPU parity of the CUDA path (through the C ABI) against fixtures generated from the unmodified
+reference, with the tolerances BASELINE.json's north_star states:
+MAS bit-exact, mel max-abs <= 1e-2 and mean-abs <= 1e-3, waveform SNR >= 35 dB."""
+import numpy as np
+import pytest
+import torch
+
+from artspeech_b200 import mas
+from oracle import mas_oracle, restate
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_mas_goldens_bit_exact():
+    for key, v, xl, yl, p1, p2 in util.mas_cases():
+        vt = torch.from_numpy(v).to(DEV)
+        keep = vt.clone()
+        xlt, ylt = torch.from_numpy(xl).to(DEV), torch.from_numpy(yl).to(DEV)
+        out2 = mas.maximum_path_lens(vt, xlt, ylt, mas.TIE_STAY).cpu().numpy()
+        out1 = mas.maximum_path_lens(vt, xlt, ylt, mas.TIE_MOVE).cpu().numpy()
+        assert np.array_equal(out2, p2), key
+        assert np.array_equal(out1, p1), key
+        assert torch.equal(vt, keep), "input must not be modified"
+
+
+def test_mas_reference_signatures():
+    key, v, xl, yl, p1, p2 = next(iter(util.mas_cases()))
+    B, Tx, Ty = v.shape
+    mask = ((np.arange(Tx)[None, :, None] < xl[:, None, None]) & (np.arange(Ty)[None, None, :] < yl[:, None, None]))
+    vt, mt = torch.from_numpy(v).to(DEV), torch.from_numpy(mask.astype(np.float32)).to(DEV)
+    assert np.array_equal(mas.maximum_path1(vt, mt).cpu().numpy(), p1)
+    assert np.array_equal(mas.maximum_path2(vt, mt).cpu().numpy(), p2)
+    assert np.array_equal(mas.maximum_path(vt, mt.bool()).cpu().numpy(), p2)
+    m2 = mas.mask_from_lens(vt, torch.from_numpy(xl).to(DEV), torch.from_numpy(yl).to(DEV))
+    assert torch.equal(m2, mt)
+
+
+@pytest.mark.parametrize("kind", ["randn", "ties"])
+def test_mas_full_size_bit_exact(kind):
+    """BASELINE config 5: 64 x 200 tokens x 1000 frames."""
+    rng = np.random.default_rng(7)
+    B, Tx, Ty = 64, 200, 1000
+    v = rng.standard_normal((B, Tx, Ty)).astype(np.float32) if kind == "randn" else \
+        rng.integers(0, 4, (B, Tx, Ty)).astype(np.float32)
+    xl = rng.integers(100, 201, B); yl = np.maximum(rng.integers(500, 1001, B), xl)
+    xl[0], yl[0] = 200, 1000
+    for tie, name in ((mas.TIE_STAY, "stay"), (mas.TIE_MOVE, "move")):
+        out = mas.maximum_path_lens(torch.from_numpy(v).to(DEV), torch.from_numpy(xl), torch.from_numpy(yl), tie)
+        ref = mas_oracle.maximum_path(v, xl, yl, name)
+        assert np.array_equal(out.cpu().numpy(), ref), (kind, name)
+        # size-independent properties: one cell per valid column, monotone, ends at the corners
+        p = out.cpu().numpy()
+        for b in range(0, B, 9):
+            cols = p[b, :, :yl[b]].sum(0)
+            assert np.all(cols == 1) and p[b, :, yl[b]:].sum() == 0 and p[b, xl[b]:, :].sum() == 0
+            rows = p[b, :, :yl[b]].argmax(0)
+            assert rows[0] == 0 or xl[b] > yl[b]
+            assert rows[-1] == xl[b] - 1 and np.all(np.diff(rows) >= 0) and np.all(np.diff(rows) <= 1)
+
+
+def test_mas_edge_cases():
+    v = torch.randn(3, 7, 9, device=DEV)
+    out = mas.maximum_path_lens(v, torch.tensor([0, 1, 7]), torch.tensor([5, 9, 7]), mas.TIE_STAY).cpu()
+    assert out[0].sum() == 0                       # empty item
+    assert torch.equal(out[1, 0], torch.ones(9)) and out[1, 1:].sum() == 0   # single token
+    assert torch.equal(out[2, :, :7], torch.eye(7)) and out[2, :, 7:].sum() == 0   # x_len == y_len: diagonal
+
+
+def test_vocoder_vs_reference_golden():
+    g = util.load_golden("vocoder_small.pt")
+    gen = util.generator(g["checkpoint_seed"]).to(DEV)
+    gen.compute_dtype = torch.bfloat16
+    wav = gen(g["mel"].to(DEV)).cpu()
+    assert wav.shape == g["wav"].shape
+    s = util.snr_db(wav, g["wav"])
+    assert s >= util.WAV_SNR_DB, f"SNR {s:.1f} dB"
+    lens = torch.tensor([24, 11])
+    wav_r = gen(g["mel"].to(DEV), lens.to(DEV)).cpu()
+    one = restate.generator_forward(util.generator(g["checkpoint_seed"]).cpu().state_dict(), g["mel"][1:2, :, :11])
+    assert util.snr_db(wav_r[1:2, :, :11 * 300], one) >= util.WAV_SNR_DB
+    assert wav_r[1, :, 11 * 300:].abs().max().item() == 0.0
+    util._MODELS.clear()
+
+
+@pytest.fixture(scope="module")
+def model_gpu():
+    g = util.load_golden("acoustic_small.pt")
+    m = util.acoustic_model(g["checkpoint_seed"])
+    m.set_compute_dtype(torch.float16)
+    m = m.to(DEV)
+    m.distribution = {k: v.to(DEV) for k, v in m.distribution.items()}
+    yield m, g
+    util._MODELS.clear()
+
+
+@pytest.mark.parametrize("case", ["a_pred_dur", "b_forced_dur", "c_short"])
+def test_acoustic_vs_reference_golden(model_gpu, case):
+    model, g = model_gpu
+    c = g["cases"][case]
+    tok, mel = c["tokens"].to(DEV), c["ref_mel"].to(DEV)
+    dur = c["out"]["pred_dur"].view(1, -1).to(DEV)      # durations fed from the reference's integer output
+    out, aux = model([tok, torch.tensor([tok.shape[1]], device=DEV), mel, torch.tensor([mel.shape[2]], device=DEV)],
+                     step="test", durations=dur, return_aux=True)
+    o = c["out"]
+    d = (out.cpu() - o["mel"]).abs()
+    assert d.max().item() <= util.MEL_MAX_ABS and d.mean().item() <= util.MEL_MEAN_ABS, (d.max().item(), d.mean().item())
+    assert (aux["style"].cpu() - o["style"]).abs().max().item() < 2e-3
+    for k in ("F0", "N", "EMA"):
+        assert (aux[k].transpose(1, 2).cpu() - o[k]).abs().max().item() < 2e-3, k
+    for k in ("f0_ext", "n_ext", "ema_ext"):
+        assert (aux[k].cpu() - o[k]).abs().max().item() < 2e-3, k
+    if case == "a_pred_dur":   # the duration predictor itself (rounding must agree with the reference)
+        out2, aux2 = model([tok, torch.tensor([tok.shape[1]], device=DEV), mel, torch.tensor([mel.shape[2]], device=DEV)],
+                           step="test", return_aux=True)
+        assert (aux2["duration"].cpu() - o["duration"]).abs().max().item() < 2e-3
+        assert torch.equal(aux2["pred_dur"].long().view(-1).cpu(), o["pred_dur"].view(-1))
+
+
+def test_ragged_batch_and_text_to_wave(model_gpu):
+    model, g = model_gpu
+    names = ["a_pred_dur", "b_forced_dur", "c_short"]
+    cs = [g["cases"][n] for n in names]
+    Tt = max(c["tokens"].shape[1] for c in cs)
+    Tr = max(c["ref_mel"].shape[2] for c in cs)
+    tok = torch.zeros(3, Tt, dtype=torch.long)
+    mel = torch.zeros(3, 80, Tr)
+    dur = torch.ones(3, Tt, dtype=torch.long)
+    for i, c in enumerate(cs):
+        tok[i, :c["tokens"].shape[1]] = c["tokens"][0]
+        mel[i, :, :c["ref_mel"].shape[2]] = c["ref_mel"][0]
+        dur[i, :c["tokens"].shape[1]] = c["out"]["pred_dur"].view(-1)
+    tl = torch.tensor([c["tokens"].shape[1] for c in cs])
+    ml = torch.tensor([c["ref_mel"].shape[2] for c in cs])
+    out, aux = model([tok.to(DEV), tl.to(DEV), mel.to(DEV), ml.to(DEV)], step="test", durations=dur.to(DEV),
+                     return_aux=True)
+    lens_m = aux["mel_lengths"].cpu()
+    for i, c in enumerate(cs):
+        Tm = c["out"]["mel"].shape[2]
+        assert int(lens_m[i]) == Tm
+        d = (out[i, :, :Tm].cpu() - c["out"]["mel"][0]).abs()
+        assert d.max().item() <= util.MEL_MAX_ABS and d.mean().item() <= util.MEL_MEAN_ABS, (names[i], d.max().item())
+    # text -> waveform: vocode our mel, compare with the fp32 oracle vocoding the reference mel
+    gen = util.generator(0).to(DEV)
+    wav = gen(out, lens_m.to(DEV)).cpu()
+    sd = util.generator(0).cpu().state_dict()
+    for i, c in enumerate(cs):
+        Tm = c["out"]["mel"].shape[2]
+        ref_wav = restate.generator_forward(sd, c["out"]["mel"])
+        s = util.snr_db(wav[i:i + 1, :, :Tm * 300], ref_wav)
+        assert s >= util.WAV_SNR_DB, f"{names[i]}: SNR {s:.1f} dB"

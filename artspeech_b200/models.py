@@ -166,7 +166,7 @@ class StyleEncoder(nn_util.PlanMixin, nn.Module):
         return (f0_cf, n_cf, ema_cf), (f0_cl, n_cl, ema_cl), style.view(B, -1)
 
     @torch.no_grad()
-    def forward(self, mel, mel_input_length, step="second", distribution=None, epoch=20, channels_last=False):
+    def forward(self, mel, mel_input_length, step="second", distribution=None, epoch=20, host_lengths=None):
         """``mel`` [B,80,T], ``mel_input_length`` [B] -> (f0 [B,1,T], n [B,1,T], ema [B,10,T], Style [B,512]).
 
         Utterances are processed in groups of equal length so each one sees exactly what a batch-1
@@ -176,8 +176,12 @@ class StyleEncoder(nn_util.PlanMixin, nn.Module):
             raise ValueError("StyleEncoder needs the normalisation statistics (Data/stats.json)")
         mel = mel.detach().float()
         B, M, T = mel.shape
-        lens = [int(v) for v in mel_input_length.tolist()]
+        # ``host_lengths`` (python ints) avoids the device->host sync of ``.tolist()``
+        lens = list(host_lengths) if host_lengths is not None else [int(v) for v in mel_input_length.tolist()]
         dev = mel.device
+        if all(v == T for v in lens):
+            (f0, n, ema), _, style = self._forward_uniform(mel, distribution)
+            return f0, n, ema, style
         f0 = torch.zeros(B, 1, T, device=dev)
         n = torch.zeros(B, 1, T, device=dev)
         ema = torch.zeros(B, 10, T, device=dev)
@@ -231,7 +235,7 @@ class DurationPredictor(nn_util.PlanMixin, nn.Module):
                                             self.duration_proj.linear_layer.bias, dt, device))
 
     @torch.no_grad()
-    def forward(self, texts, style, text_lengths, mel_input_length):
+    def forward(self, texts, style, text_lengths, mel_input_length, host_mel_lengths=None):
         """``texts`` [B,Tt], ``style`` = normalised EMA [B,10,Tr] -> duration fp32 [B,Tt]
         (models.py:540-566).  Every utterance's dur_block sees its full padded EMA row, as the
         reference's per-utterance loop does (:543-545)."""
@@ -242,7 +246,10 @@ class DurationPredictor(nn_util.PlanMixin, nn.Module):
         lens = _i32(text_lengths, dev)
         style = style.detach().float()
         Tr = style.shape[2]
-        mlens = [Tr] * B if mel_input_length is None else [min(int(v), Tr) for v in mel_input_length.tolist()]
+        if host_mel_lengths is not None:
+            mlens = [min(int(v), Tr) for v in host_mel_lengths]
+        else:
+            mlens = [Tr] * B if mel_input_length is None else [min(int(v), Tr) for v in mel_input_length.tolist()]
         dstyle = torch.empty(B, self.style_dim // 4, dtype=dt, device=dev)
         for L in sorted(set(mlens)):                                          # batch-1 semantics: crop to own length
             idx = [i for i, v in enumerate(mlens) if v == L]
@@ -502,7 +509,10 @@ class ArtsSpeech(nn.Module):
 
     @torch.no_grad()
     def forward(self, batch, s2s_attn=None, s2s_attn_mono=None, step="test", mode="train", epoch=0,
-                durations: Optional[torch.Tensor] = None, return_aux: bool = False):
+                durations: Optional[torch.Tensor] = None, return_aux: bool = False, host_meta: Optional[dict] = None):
+        """``host_meta`` (optional, keeps the pass free of device->host syncs so it can be captured in
+        a CUDA graph): ``{"mel_lens": [int], "Lmax": int}`` = reference-mel lengths and the largest
+        ``sum(durations[b, :len_b])``; requires ``durations``."""
         if step != "test":
             raise NotImplementedError("artspeech_b200 accelerates the synthesis path (step='test'); the "
                                       "training branches (models.py:291-354) stay with the reference")
@@ -515,9 +525,12 @@ class ArtsSpeech(nn.Module):
 
         T_en = self.text_encoder(texts, input_lengths)                                   # [B,Tt,512] fp32 (:357)
         A_en = self.arts_encoder(texts, input_lengths)                                   # (:358)
-        f0_ext, n_ext, ema_ext, style = self.style_encoder(mels, mel_input_length, "second", self.distribution)
+        hm = host_meta or {}
+        f0_ext, n_ext, ema_ext, style = self.style_encoder(mels, mel_input_length, "second", self.distribution,
+                                                           host_lengths=hm.get("mel_lens"))
         if durations is None:
-            duration = self.durationPredictor(texts, ema_ext, input_lengths, mel_input_length)   # (:360)
+            duration = self.durationPredictor(texts, ema_ext, input_lengths, mel_input_length,
+                                              host_mel_lengths=hm.get("mel_lens"))                # (:360)
             pred_dur = torch.round(duration).clamp(min=1)                                # half-to-even (:361)
         else:
             duration = None
@@ -525,9 +538,11 @@ class ArtsSpeech(nn.Module):
         dur = pred_dur.to(torch.int32).contiguous()
         if dur.dim() == 1:
             dur = dur.view(1, -1)
-        valid = torch.arange(Tt, device=dev)[None, :] < lens_t[:, None]
-        L = (dur * valid).sum(dim=1)
-        Lmax = int(L.max().item())                                                       # one host sync (ref: 2*Tt+1)
+        if "Lmax" in hm and durations is not None:
+            Lmax = int(hm["Lmax"])
+        else:
+            valid = torch.arange(Tt, device=dev)[None, :] < lens_t[:, None]
+            Lmax = int((dur * valid).sum(dim=1).max().item())                            # one host sync (ref: 2*Tt+1)
         Tm = 2 * Lmax
 
         style16 = style.to(dt).contiguous()

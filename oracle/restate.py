@@ -252,23 +252,16 @@ def bn_eval(sd, pre, x):
 
 
 def bilstm(sd, pre, x, lengths=None):
-    """Single-layer bidirectional LSTM, batch_first, PyTorch gate order (i,f,g,o); with ``lengths``
-    it has pack_padded_sequence semantics (models.py:555-564)."""
-    B, T, _ = x.shape
+    """Single-layer bidirectional LSTM, batch_first (PyTorch gate order i,f,g,o) run through
+    torch's own nn.LSTM with the state-dict's weights, like the reference does; with ``lengths`` it
+    is wrapped in pack_padded_sequence / pad_packed_sequence (models.py:555-564)."""
     H = sd[f"{pre}.weight_hh_l0"].shape[1]
-    out = torch.zeros(B, T, 2 * H)
-    for d, sfx in enumerate(("", "_reverse")):
-        wih, whh = sd[f"{pre}.weight_ih_l0{sfx}"].float(), sd[f"{pre}.weight_hh_l0{sfx}"].float()
-        bias = sd[f"{pre}.bias_ih_l0{sfx}"].float() + sd[f"{pre}.bias_hh_l0{sfx}"].float()
-        xp = x @ wih.t() + bias
-        for b in range(B):
-            L = T if lengths is None else int(lengths[b])
-            h, c = torch.zeros(H), torch.zeros(H)
-            for t in (range(L) if d == 0 else range(L - 1, -1, -1)):
-                i, f, g, o = (xp[b, t] + whh @ h).split(H)
-                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-                h = torch.sigmoid(o) * torch.tanh(c)
-                out[b, t, d * H:(d + 1) * H] = h
+    lstm = torch.nn.LSTM(x.shape[-1], H, 1, batch_first=True, bidirectional=True)
+    lstm.load_state_dict({k: sd[f"{pre}.{k}"].float() for k in lstm.state_dict()})
+    if lengths is None:
+        return lstm(x)[0]
+    packed = torch.nn.utils.rnn.pack_padded_sequence(x, lengths.cpu(), batch_first=True, enforce_sorted=False)
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=x.shape[1])
     return out
 
 

@@ -12,8 +12,11 @@
 // Both operands use the canonical K-major 128B (BK=64) / 64B (BK=32) swizzled layout that TMA
 // writes and the UMMA shared-memory descriptor reads.  fp32 accumulators live in TMEM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
-// issuer (one lane), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Persistent CTAs (grid = #SMs x CTAs/SM) walk a static tile schedule.  Warp roles (320 threads):
+// warp 0 = TMA producer (one lane, runs ahead across tiles through the smem ring), warp 1 = TMEM
+// allocator + MMA issuer (one lane, alternates between two TMEM accumulator stages), warps 2..9 =
+// two epilogue warpgroups that drain the accumulator stages alternately (TMEM lane quadrant =
+// warp_idx % 4), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <string.h>
 
@@ -21,7 +24,7 @@
 
 namespace asb {
 
-constexpr int CV_THREADS = 192;
+constexpr int CV_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups
 constexpr int CV_MAX_TAPS = 32;
 
 struct ConvArgs {
@@ -202,32 +205,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int W_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);   // two accumulator stages (power of two)
 
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int S = a.stages;
-  const uint32_t bar_base = smem_base + S * STAGE_BYTES;  // full[S], empty[S], tmem_full, slot
+  const uint32_t bar_base = smem_base + S * STAGE_BYTES;  // full[S], empty[S], tfull[2], tempty[2], slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int mt = blockIdx.x;
-  const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
-  const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
-  const int b = mt;
-  const int t0 = tt * a.tT, f0 = ft * a.tF;
-  const int n0 = blockIdx.y * BN;
+  const int m_tiles = a.B * a.n_ttiles * a.n_ftiles;
+  const int total_tiles = m_tiles * (a.CoutP / BN);
   const int k_iters = a.ntaps * a.kchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -246,88 +244,120 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  // Persistent CTA: every role walks the same static tile schedule (tile = blockIdx.x + i*gridDim.x,
+  // M fastest so concurrently running CTAs share the weight tile in L2).  The smem ring and the two
+  // TMEM accumulator stages decouple the roles: TMA runs ahead across tile boundaries, the MMA of
+  // tile i+1 overlaps the epilogue of tile i.
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        const int tap = it / a.kchunks, kc = it - tap * a.kchunks;
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        tma_load_4d(sa, &tmA, full_bar(s), kc * BK, f0 + a.tap_df[tap], t0 + a.tap_dt[tap], b);
-        tma_load_2d(sa + A_BYTES, &tmW, full_bar(s), kc * BK, tap * a.CoutP + n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt = tile % m_tiles;
+        const int n0 = (tile / m_tiles) * BN;
+        const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
+        const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
+        const int b = mt, t0 = tt * a.tT, f0 = ft * a.tF;
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const int tap = kit / a.kchunks, kc = kit - tap * a.kchunks;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          tma_load_4d(sa, &tmA, full_bar(s), kc * BK, f0 + a.tap_df[tap], t0 + a.tap_dt[tap], b);
+          tma_load_2d(sa + A_BYTES, &tmW, full_bar(s), kc * BK, tap * a.CoutP + n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue drained this stage
         tc_fence_after();
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint64_t da = make_smem_desc<BK>(sa);
-        const uint64_t db = make_smem_desc<BK>(sa + A_BYTES);
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint64_t da = make_smem_desc<BK>(sa);
+          const uint64_t db = make_smem_desc<BK>(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 field
-          tc_mma_f16(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc,
-                     (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 field
+            tc_mma_f16(tacc, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc, (kit | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
         }
-        tc_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+        tc_commit(tfull_bar(acc));  // accumulator of this tile complete
       }
-      tc_commit(tmem_full_bar);   // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: two warpgroups alternate tiles; TMEM -> registers -> global =====
+    const int wg = (warp - 2) >> 2;  // 0 / 1 = accumulator stage this warpgroup drains
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;     // tile row
     const int it_ = m / a.tF, if_ = m - it_ * a.tF;
-    const int t = t0 + it_, f = f0 + if_;
-    const bool row_ok = (t < a.To) && (f < a.Fo);
-    bool masked = false;
-    if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
-    const long long row = ((long long)b * a.To + t) * a.Fo + f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != wg) continue;
+      int mt = tile % m_tiles;
+      const int n0 = (tile / m_tiles) * BN;
+      const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
+      const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
+      const int b = mt;
+      const int t = tt * a.tT + it_, f = ft * a.tF + if_;
+      const bool row_ok = (t < a.To) && (f < a.Fo);
+      bool masked = false;
+      if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
+      const long long row = ((long long)b * a.To + t) * a.Fo + f;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
-    const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (c0 >= ncols) break;  // warp-uniform
-      uint32_t r[16];
-      tc_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
-      tc_wait_ld();
-      if (!row_ok) continue;
-      const int co = n0 + c0;
-      const int nvalid = min(16, a.Cout - co);
-      float v[16];
+      mbar_wait(tfull_bar(wg), ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
+      const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (c0 >= ncols) break;  // warp-uniform
+        uint32_t r[16];
+        tc_ld16(tacc + uint32_t(c0), r);
+        tc_wait_ld();
+        if (!row_ok) continue;
+        const int co = n0 + c0;
+        const int nvalid = min(16, a.Cout - co);
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      if (a.bias != nullptr) {
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (a.bias != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
+          for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
+        }
+        if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid,
+                                         (a.y_raw_vec >> 8) & 1);
+        if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid,
+                                         (a.y_raw_vec >> 9) & 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
+        if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid,
+                                        a.y_raw_vec & 1);
+        if (a.y_act != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+          store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, a.y_act_vec & 1);
+        }
       }
-      if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid,
-                                       (a.y_raw_vec >> 8) & 1);
-      if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid,
-                                       (a.y_raw_vec >> 9) & 1);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
-      if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid,
-                                      a.y_raw_vec & 1);
-      if (a.y_act != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-        store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, a.y_act_vec & 1);
-      }
+      // all TMEM reads of this stage are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
     }
-    tc_fence_before();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -371,22 +401,38 @@ static int pick_tile_n(int Cout) {
   return p128 < p256 ? 128 : 256;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int BK>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs& a, dim3 grid,
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs& a, int total_tiles,
                        cudaStream_t st) {
   constexpr int STAGE_BYTES = 128 * BK * 2 + BN * BK * 2;
+  // BN = 256 needs all 512 TMEM columns (two accumulator stages): one CTA per SM with a deep ring.
+  // Narrower tiles run two CTAs per SM (TMEM 2*BN <= 256 columns each, ~100 KB of ring each).
+  const int ctas_per_sm = BN >= 256 ? 1 : 2;
   const int budget = (BN >= 256 ? 196 : 98) * 1024;
   int stages = budget / STAGE_BYTES;
-  if (stages > 8) stages = 8;
+  if (stages > 10) stages = 10;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 2) + 1024;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 5) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
     attr_set = true;
   }
+  int grid = num_sms() * ctas_per_sm;
+  if (grid > total_tiles) grid = total_tiles;
   conv_igemm_kernel<BN, BK><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
@@ -486,10 +532,10 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
     ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
 
-  dim3 grid((unsigned)(p->B * a.n_ttiles * a.n_ftiles), (unsigned)(p->CoutP / bn), 1);
+  const int total_tiles = p->B * a.n_ttiles * a.n_ftiles * (p->CoutP / bn);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define CV_CASE(BN_, BK_) \
-  if (bn == BN_ && bk == BK_) return launch_conv<BN_, BK_>(tmA, tmW, a, grid, st);
+  if (bn == BN_ && bk == BK_) return launch_conv<BN_, BK_>(tmA, tmW, a, total_tiles, st);
   CV_CASE(16, 32) CV_CASE(32, 32) CV_CASE(64, 32) CV_CASE(128, 32) CV_CASE(256, 32)
   CV_CASE(16, 64) CV_CASE(32, 64) CV_CASE(64, 64) CV_CASE(128, 64) CV_CASE(256, 64)
 #undef CV_CASE

@@ -46,12 +46,13 @@ def test_vocoder_restatement_and_host_logic(sim):
 
 
 @pytest.mark.parametrize("case", ["a_pred_dur", "b_forced_dur", "c_short"])
-def test_acoustic_host_logic_fp32_exact(sim, case):
+def test_acoustic_host_logic_fp32_exact(sim, monkeypatch, case):
     """With fp32 'operands' the dataflow must reproduce the reference to rounding noise: this pins
     weight folding, layouts, tap tables, fused concats, masks and the batched style FCs."""
     g = util.load_golden("acoustic_small.pt")
     model = util.acoustic_model(g["checkpoint_seed"])
     model.set_compute_dtype(torch.float32)
+    monkeypatch.setattr(sim, "EMULATE_FP16_RECURRENCE", False)
     c = g["cases"][case]
     tok, mel = c["tokens"], c["ref_mel"]
     out, aux = model([tok, torch.tensor([tok.shape[1]]), mel, torch.tensor([mel.shape[2]])], step="test",
@@ -81,11 +82,12 @@ def test_acoustic_fp16_within_tolerance(sim):
     assert d.max().item() <= util.MEL_MAX_ABS and d.mean().item() <= util.MEL_MEAN_ABS
 
 
-def test_ragged_batch_equals_batch1(sim):
+def test_ragged_batch_equals_batch1(sim, monkeypatch):
     """B=3 with different token / reference lengths must equal three batch-1 reference runs."""
     g = util.load_golden("acoustic_small.pt")
     model = util.acoustic_model(g["checkpoint_seed"])
     model.set_compute_dtype(torch.float32)
+    monkeypatch.setattr(sim, "EMULATE_FP16_RECURRENCE", False)
     names = ["a_pred_dur", "b_forced_dur", "c_short"]
     cs = [g["cases"][n] for n in names]
     Tt = max(c["tokens"].shape[1] for c in cs)

@@ -33,7 +33,7 @@ def _fingerprint() -> str:
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files.append(os.path.join(HERE, "..", "include", "artspeech_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())     # content-addressed: the repo may live anywhere
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

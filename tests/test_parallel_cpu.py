@@ -1,0 +1,73 @@
+"""Data-parallel host logic on CPU: LPT sharding and the waveform gather over a 2-rank gloo group
+(the only collective on the path; NCCL on the GPU box uses the same code)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from artspeech_b200 import engine
+
+
+def test_lpt_sharding_balances_and_covers():
+    g = torch.Generator().manual_seed(0)
+    costs = torch.randint(15, 600, (512,), generator=g).tolist()
+    for world in (1, 2, 4, 8):
+        shards = engine.shard_utterances(costs, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(512))                      # every utterance exactly once
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(costs)          # LPT bound
+    assert engine.shard_utterances([], 4) == [[], [], [], []]
+    assert engine.shard_utterances([5.0], 2) == [[0], []]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        costs = [800, 300, 650, 120, 480]
+        mine = engine.shard_utterances(costs, world)[rank]
+        # stand-in "waveforms": utterance i has costs[i]*3 samples filled with i+1
+        S = max([costs[i] * 3 for i in mine], default=1)
+        wav = torch.zeros(len(mine), S)
+        lens = torch.zeros(len(mine), dtype=torch.int64)
+        for r, i in enumerate(mine):
+            wav[r, :costs[i] * 3] = i + 1
+            lens[r] = costs[i] * 3
+        wavs, lns = engine.gather_waveforms(wav, lens, dst=0)
+        if rank == 0:
+            shards = engine.shard_utterances(costs, world)
+            ok = True
+            for r in range(world):
+                for row, i in enumerate(shards[r]):
+                    n = int(lns[r][row])
+                    ok &= n == costs[i] * 3 and bool((wavs[r][row, :n] == i + 1).all()) and \
+                        bool((wavs[r][row, n:] == 0).all())
+            q.put(ok)
+        else:
+            assert wavs is None and lns is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_waveforms_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -43,6 +43,9 @@ struct ConvArgs {
   int act; float slope;
   const int* lens;
   float* stats;
+  // fast-epilogue plan (host-computed): tensor kinds 0 absent / 1 launch 16-bit format / 2 fp32
+  int fast, k_res1, k_res2, k_raw, k_act, act_simple;
+  float act_slope_eff;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -195,10 +198,59 @@ __device__ __forceinline__ void add_res16(const void* base, int dtype, long long
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast epilogue chunk (16 channels of one row).  The generic helpers above dispatch on dtypes per
+// element and cost ~500 SASS instructions per chunk (ncu: the epilogue, not the MMAs, bounded the
+// kernel).  This path is specialised at compile time on the 16-bit format and hoists every
+// decision out of the chunk loop: ~120 instructions per chunk.
+//   kind: 0 = absent, 1 = 16-bit (the launch's operand format), 2 = fp32
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) { __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <bool BF16>
+__device__ __forceinline__ void unpack_add(uint32_t u, float& a, float& b) {
+  if (BF16) { a += __uint_as_float(u << 16); b += __uint_as_float(u & 0xFFFF0000u); return; }
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+  a += f.x; b += f.y;
+}
+template <bool BF16>
+__device__ __forceinline__ void add_res_fast(const char* p, int kind, float (&v)[16]) {
+  if (kind == 1) {
+    const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(p)), t1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+    unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+    unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+    unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ void store_fast(char* p, int kind, const float (&v)[16]) {
+  if (kind == 1) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+    q[1] = make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15]));
+  } else {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int BK>
+template <int BN, int BK, bool BF16>
 __global__ void __launch_bounds__(CV_THREADS)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ ConvArgs a) {
@@ -317,10 +369,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
       const long long row = ((long long)b * a.To + t) * a.Fo + f;
 
+      // per-tile constants of the fast path (byte pointers of this thread's row, kinds, slope)
+      const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
+      const bool fast = a.fast != 0;
+      const int k_r1 = a.k_res1, k_r2 = a.k_res2, k_raw = a.k_raw, k_act = a.k_act;
+      const char* p_r1 = k_r1 ? reinterpret_cast<const char*>(a.res1) + (row * a.res1_ld + n0) * (k_r1 == 1 ? 2 : 4) : nullptr;
+      const char* p_r2 = k_r2 ? reinterpret_cast<const char*>(a.res2) + (row * a.res2_ld + n0) * (k_r2 == 1 ? 2 : 4) : nullptr;
+      char* p_raw = k_raw ? reinterpret_cast<char*>(a.y_raw) + (row * a.y_raw_ld + n0) * (k_raw == 1 ? 2 : 4) : nullptr;
+      char* p_act = k_act ? reinterpret_cast<char*>(a.y_act) + (row * a.y_act_ld + n0) * (k_act == 1 ? 2 : 4) : nullptr;
+      const float scale = masked ? 0.f : a.out_scale;   // masked rows become exact zeros (res are finite)
+      const float aslope = a.act_slope_eff;
+
       mbar_wait(tfull_bar(wg), ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
-      const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
       for (int c0 = 0; c0 < BN; c0 += 16) {
         if (c0 >= ncols) break;  // warp-uniform
         uint32_t r[16];
@@ -328,26 +390,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_wait_ld();
         if (!row_ok) continue;
         const int co = n0 + c0;
-        const int nvalid = min(16, a.Cout - co);
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (a.bias != nullptr) {
+        if (fast && c0 + 16 <= ncols) {
+          if (a.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
-        }
-        if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid,
-                                         (a.y_raw_vec >> 8) & 1);
-        if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid,
-                                         (a.y_raw_vec >> 9) & 1);
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + co) + i);
+              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+            }
+          }
+          if (k_r1 && !masked) add_res_fast<BF16>(p_r1 + c0 * (k_r1 == 1 ? 2 : 4), k_r1, v);
+          if (k_r2 && !masked) add_res_fast<BF16>(p_r2 + c0 * (k_r2 == 1 ? 2 : 4), k_r2, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
-        if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid,
-                                        a.y_raw_vec & 1);
-        if (a.y_act != nullptr) {
+          for (int i = 0; i < 16; ++i) v[i] *= scale;
+          if (k_raw) store_fast<BF16>(p_raw + c0 * (k_raw == 1 ? 2 : 4), k_raw, v);
+          if (k_act) {
+            if (a.act_simple) {
+              // none / lrelu / relu / abs: act(v) = max(v, v * s) with s = 1 / slope / 0 / -1
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-          store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, a.y_act_vec & 1);
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * aslope);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+            }
+            store_fast<BF16>(p_act + c0 * (k_act == 1 ? 2 : 4), k_act, v);
+          }
+        } else {
+          // generic path: partial chunks (Cout not a multiple of 16), unaligned or mixed-format tensors
+          const int nvalid = min(16, a.Cout - co);
+          if (a.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
+          }
+          if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid, false);
+          if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid, false);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
+          if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid, false);
+          if (a.y_act != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+            store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, false);
+          }
         }
       }
       // all TMEM reads of this stage are complete (tcgen05.wait::ld above): hand it back to the MMA warp
@@ -412,7 +498,7 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool BF16>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs& a, int total_tiles,
                        cudaStream_t st) {
   constexpr int STAGE_BYTES = 128 * BK * 2 + BN * BK * 2;
@@ -427,13 +513,13 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs&
   const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 5) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK>,
+    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, BF16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
     attr_set = true;
   }
   int grid = num_sms() * ctas_per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_igemm_kernel<BN, BK><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  conv_igemm_kernel<BN, BK, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -505,6 +591,30 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
   a.act = p->act; a.slope = p->slope;
   a.lens = p->lens;
   a.stats = p->stats;
+  {
+    // fast epilogue: every present tensor is fp32 or the launch's 16-bit format, 16-byte aligned rows
+    auto kind = [&](const void* ptr, int dtype, long long ld) -> int {
+      if (ptr == nullptr) return 0;
+      if (!vec_ok(ptr, ld, dtype)) return -1;
+      if (dtype == AS_F32) return 2;
+      return dtype == p->x_dtype ? 1 : -1;
+    };
+    a.k_res1 = kind(p->res1, p->res1_dtype, p->res1_ld);
+    a.k_res2 = kind(p->res2, p->res2_dtype, p->res2_ld);
+    a.k_raw = kind(p->y_raw, p->y_raw_dtype, p->y_raw_ld);
+    a.k_act = kind(p->y_act, p->y_act_dtype, p->y_act_ld);
+    const bool bias_ok = p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
+    a.fast = (a.k_res1 >= 0 && a.k_res2 >= 0 && a.k_raw >= 0 && a.k_act >= 0 && bias_ok) ? 1 : 0;
+    if (!a.fast) { a.k_res1 = a.k_res2 = a.k_raw = a.k_act = 0; }
+    a.act_simple = 1;
+    switch (p->act) {
+      case AS_ACT_NONE: a.act_slope_eff = 1.f; break;
+      case AS_ACT_LRELU: a.act_slope_eff = p->slope; a.act_simple = (p->slope <= 1.f) ? 1 : 0; break;
+      case AS_ACT_RELU: a.act_slope_eff = 0.f; break;
+      case AS_ACT_ABS: a.act_slope_eff = -1.f; break;
+      default: a.act_simple = 0; a.act_slope_eff = 1.f; break;
+    }
+  }
 
   const CUtensorMapDataType dt =
       p->x_dtype == AS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -534,8 +644,10 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
 
   const int total_tiles = p->B * a.n_ttiles * a.n_ftiles * (p->CoutP / bn);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CV_CASE(BN_, BK_) \
-  if (bn == BN_ && bk == BK_) return launch_conv<BN_, BK_>(tmA, tmW, a, total_tiles, st);
+#define CV_CASE(BN_, BK_)                                                                    \
+  if (bn == BN_ && bk == BK_)                                                                \
+    return p->x_dtype == AS_BF16 ? launch_conv<BN_, BK_, true>(tmA, tmW, a, total_tiles, st) \
+                                 : launch_conv<BN_, BK_, false>(tmA, tmW, a, total_tiles, st);
   CV_CASE(16, 32) CV_CASE(32, 32) CV_CASE(64, 32) CV_CASE(128, 32) CV_CASE(256, 32)
   CV_CASE(16, 64) CV_CASE(32, 64) CV_CASE(64, 64) CV_CASE(128, 64) CV_CASE(256, 64)
 #undef CV_CASE

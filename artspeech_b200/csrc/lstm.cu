@@ -15,6 +15,9 @@ namespace asb {
 constexpr int LSTM_BG = 4;  // batch items per CTA
 
 __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); }
+// MUFU-based variants for the per-step critical path of the tensor-core kernels (abs error ~1e-6)
+__device__ __forceinline__ float fsigm(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float ftanh(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
 
 template <int BG>
 __global__ void __launch_bounds__(1024, 1) bilstm_kernel(const float* __restrict__ xproj, long long xp_ld,
@@ -179,27 +182,33 @@ bilstm128_mma_kernel(const float* __restrict__ xproj, long long xp_ld,
     const int t = dir == 0 ? s : len - 1 - s;
     return __ldg(xproj + ((long long)(b0 + n) * T + t) * xp_ld + (long long)dir * G + q * H + j);
   };
-  float xn[4][4];  // prefetched input projections for the next step: [gate][element]
+  // input projections are prefetched PF steps ahead (register ring; the loop is unrolled by PF so
+  // the ring slots are compile-time): the L2 latency of the 16 scattered loads hides behind PF steps.
+  constexpr int PF = 4;
+  float xn[PF][4][4];
+  auto fetch = [&](float (&dst)[4][4], int s) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    xn[q][0] = xp_at(n0, len0, 0, q, j0); xn[q][1] = xp_at(n0 + 1, len1, 0, q, j0);
-    xn[q][2] = xp_at(n0, len0, 0, q, j1); xn[q][3] = xp_at(n0 + 1, len1, 0, q, j1);
-  }
+    for (int q = 0; q < 4; ++q) {
+      dst[q][0] = xp_at(n0, len0, s, q, j0); dst[q][1] = xp_at(n0 + 1, len1, s, q, j0);
+      dst[q][2] = xp_at(n0, len0, s, q, j1); dst[q][3] = xp_at(n0 + 1, len1, s, q, j1);
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < PF; ++u) fetch(xn[u], u);
 
-  for (int s = 0; s < maxlen; ++s) {
+  for (int s0 = 0; s0 < maxlen; s0 += PF) {
+#pragma unroll
+   for (int u = 0; u < PF; ++u) {
+    const int s = s0 + u;
+    if (s >= maxlen) break;
     const __half* hp = &hs[s & 1][0][0];
     __half* hn = &hs[(s + 1) & 1][0][0];
     float acc[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[q][e] = xn[q][e];
-    // prefetch step s+1 while the tensor cores work
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      xn[q][0] = xp_at(n0, len0, s + 1, q, j0); xn[q][1] = xp_at(n0 + 1, len1, s + 1, q, j0);
-      xn[q][2] = xp_at(n0, len0, s + 1, q, j1); xn[q][3] = xp_at(n0 + 1, len1, s + 1, q, j1);
-    }
+      for (int e = 0; e < 4; ++e) acc[q][e] = xn[u][q][e];
+    fetch(xn[u], s + PF);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
       // B fragment: B[k][n] = h[n][k]; b0 -> k = 16ks + 2tig (+1), b1 -> +8, n = gid
@@ -214,15 +223,173 @@ bilstm128_mma_kernel(const float* __restrict__ xproj, long long xp_ld,
       const int n = n0 + (e & 1), j = (e < 2) ? j0 : j1;
       const int len = (e & 1) ? len1 : len0;
       if (s < len) {
-        const float ig = sigm(acc[0][e]), fg = sigm(acc[1][e]), gg = tanhf(acc[2][e]), og = sigm(acc[3][e]);
+        const float ig = fsigm(acc[0][e]), fg = fsigm(acc[1][e]), gg = ftanh(acc[2][e]), og = fsigm(acc[3][e]);
         c[e] = fg * c[e] + ig * gg;
-        const float hval = og * tanhf(c[e]);
+        const float hval = og * ftanh(c[e]);
         hn[n * L128_HP + j] = __float2half_rn(hval);
         const int t = dir == 0 ? s : len - 1 - s;
         stany(out, ((long long)(b0 + n) * T + t) * out_ld + dir * H + j, hval, odt);
       }
     }
     __syncthreads();
+   }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// H = 256 (duration predictor, JDCNet): W_hh in fp16 is 512 KB, more than one SM can hold.  A
+// cluster of 4 CTAs splits the hidden units (64 each); every CTA keeps its 256 gate rows x 256 k as
+// register-resident mma fragments (128 regs/thread), computes its units' gates with mma.sync
+// m16n8k16 and broadcasts the new h (fp16) into all four CTAs' shared tiles through DSMEM
+// (st.shared::cluster); one cluster barrier per step.  Warp w owns 8 units for all four gates:
+// tile 0 = (i | f) x 8 units, tile 1 = (g | o) x 8 units, so i,f,g,o of a (unit, batch item) meet in
+// one thread and the cell update is register-only (fp32).  8 batch items per cluster.
+// ---------------------------------------------------------------------------------------------
+constexpr int L256_H = 256;
+constexpr int L256_NB = 8;
+constexpr int L256_NC = 4;     // CTAs per cluster
+constexpr int L256_HP = 264;   // padded pitch (halves) of the h tile
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(L256_NC, 1, 1) __launch_bounds__(256, 1)
+bilstm256_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
+                         const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T,
+                         const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  constexpr int H = L256_H, G = 4 * H;
+  __shared__ __align__(16) __half hs[2][L256_NB][L256_HP];
+  __shared__ int s_len[L256_NB];
+  const int dir = blockIdx.y;
+  const uint32_t crank = cluster_rank();
+  const int b0 = (blockIdx.x / L256_NC) * L256_NB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const float* Wt = whh_t + (long long)dir * H * G;      // Wt[k][row]
+  const int unit = (int)crank * 64 + warp * 8 + gid;    // this thread's hidden unit
+
+  if (threadIdx.x < L256_NB) {
+    const int b = b0 + threadIdx.x;
+    s_len[threadIdx.x] = (b < B) ? (lens ? min(lens[b], T) : T) : 0;
+  }
+  for (int i = threadIdx.x; i < 2 * L256_NB * L256_HP; i += blockDim.x) (&hs[0][0][0])[i] = __float2half(0.f);
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int i = 0; i < L256_NB; ++i) maxlen = max(maxlen, s_len[i]);
+
+  // A fragments: tile tq rows 0..7 = gate 2tq, rows 8..15 = gate 2tq+1, both for units warp*8 + (row & 7)
+  uint32_t afrag[2][16][4];
+#pragma unroll
+  for (int tq = 0; tq < 2; ++tq) {
+    const int r_lo = (2 * tq) * H + unit, r_hi = (2 * tq + 1) * H + unit;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      const int k0 = 16 * ks + 2 * tig;
+      auto pk = [&](int r, int k) {
+        __half2 v = __floats2half2_rn(Wt[(long long)k * G + r], Wt[(long long)(k + 1) * G + r]);
+        return *reinterpret_cast<uint32_t*>(&v);
+      };
+      afrag[tq][ks][0] = pk(r_lo, k0);
+      afrag[tq][ks][1] = pk(r_hi, k0);
+      afrag[tq][ks][2] = pk(r_lo, k0 + 8);
+      afrag[tq][ks][3] = pk(r_hi, k0 + 8);
+    }
+  }
+  const int n0 = 2 * tig;
+  const int len0 = s_len[n0], len1 = s_len[n0 + 1];
+  float c[2] = {0.f, 0.f};   // (unit, n0), (unit, n0+1)
+
+  // zero the padded tail of the output for this CTA's 64 units
+  for (int i = 0; i < L256_NB; ++i) {
+    const int b = b0 + i;
+    if (b >= B) continue;
+    for (long long e = (long long)s_len[i] * 64 + threadIdx.x; e < (long long)T * 64; e += blockDim.x)
+      stany(out, ((long long)b * T + e / 64) * out_ld + dir * H + crank * 64 + (e % 64), 0.f, odt);
+  }
+
+  auto xp_at = [&](int n, int len, int s, int gate) -> float {
+    if (s >= len) return 0.f;
+    const int t = dir == 0 ? s : len - 1 - s;
+    return __ldg(xproj + ((long long)(b0 + n) * T + t) * xp_ld + (long long)dir * G + gate * H + unit);
+  };
+  constexpr int PF = 2;
+  float xn[PF][4][2];   // [slot][gate][batch element]
+  auto fetch = [&](float (&dst)[4][2], int s) {
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) { dst[g4][0] = xp_at(n0, len0, s, g4); dst[g4][1] = xp_at(n0 + 1, len1, s, g4); }
+  };
+#pragma unroll
+  for (int u = 0; u < PF; ++u) fetch(xn[u], u);
+
+  // remote addresses of this thread's h slot in each CTA of the cluster (even gid lanes publish batch
+  // n0, odd gid lanes batch n0+1; each packs two adjacent units into one 32-bit DSMEM store)
+  const int pub_n = (gid & 1) ? n0 + 1 : n0;
+  const int pub_unit = unit & ~1;
+  uint32_t raddr[L256_NC];
+#pragma unroll
+  for (int r = 0; r < L256_NC; ++r) raddr[r] = mapa_shared(smem_u32(&hs[0][pub_n][pub_unit]), (uint32_t)r);
+  constexpr uint32_t BUF_BYTES = L256_NB * L256_HP * 2;
+
+  cluster_sync_all();   // every CTA has zeroed its tiles before anyone publishes into them
+
+  for (int s0 = 0; s0 < maxlen; s0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int s = s0 + u;
+      if (s >= maxlen) break;
+      const __half* hp = &hs[s & 1][0][0];
+      float acc[2][4];
+      acc[0][0] = xn[u][0][0]; acc[0][1] = xn[u][0][1]; acc[0][2] = xn[u][1][0]; acc[0][3] = xn[u][1][1];
+      acc[1][0] = xn[u][2][0]; acc[1][1] = xn[u][2][1]; acc[1][2] = xn[u][3][0]; acc[1][3] = xn[u][3][1];
+      fetch(xn[u], s + PF);
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        const uint32_t bb0 = *reinterpret_cast<const uint32_t*>(hp + gid * L256_HP + 16 * ks + 2 * tig);
+        const uint32_t bb1 = *reinterpret_cast<const uint32_t*>(hp + gid * L256_HP + 16 * ks + 2 * tig + 8);
+        mma16816(acc[0], afrag[0][ks], bb0, bb1);
+        mma16816(acc[1], afrag[1][ks], bb0, bb1);
+      }
+      float hv[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int len = e ? len1 : len0;
+        hv[e] = 0.f;
+        if (s < len) {
+          const float ig = fsigm(acc[0][e]), fg = fsigm(acc[0][2 + e]), gg = ftanh(acc[1][e]), og = fsigm(acc[1][2 + e]);
+          c[e] = fg * c[e] + ig * gg;
+          hv[e] = og * ftanh(c[e]);
+          const int t = dir == 0 ? s : len - 1 - s;
+          stany(out, ((long long)(b0 + n0 + e) * T + t) * out_ld + dir * H + unit, hv[e], odt);
+        }
+      }
+      // pack two adjacent units per lane pair (gid, gid^1) and publish to all CTAs of the cluster
+      const float send = (gid & 1) ? hv[0] : hv[1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      __half2 pk2 = (gid & 1) ? __floats2half2_rn(recv, hv[1]) : __floats2half2_rn(hv[0], recv);
+      const int plen = (gid & 1) ? len1 : len0;
+      if (s < plen) {
+        const uint32_t off = ((s + 1) & 1) ? BUF_BYTES : 0u;
+#pragma unroll
+        for (int r = 0; r < L256_NC; ++r) st_cluster_u32(raddr[r] + off, *reinterpret_cast<uint32_t*>(&pk2));
+      }
+      cluster_sync_all();
+    }
   }
 }
 
@@ -235,10 +402,17 @@ extern "C" int as_bilstm(const float* xproj, int64_t xproj_ld, const float* whh,
                          int64_t out_ld, void* stream) {
   if (B * T == 0) return AS_OK;
   ASB_REQUIRE(xproj && whh && out, AS_ERR_SHAPE, "as_bilstm: null pointer");
-  ASB_REQUIRE(H == 128 || H == 256, AS_ERR_SHAPE, "as_bilstm: hidden size %d unsupported (128 or 256)", H);
+  ASB_REQUIRE(H == 128 || H == 256 || H == 64, AS_ERR_SHAPE, "as_bilstm: hidden size %d unsupported (64, 128 or 256)", H);
   if (H == 128) {
     dim3 grid128((B + L128_NB - 1) / L128_NB, 2);
     bilstm128_mma_kernel<<<grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld);
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
+  if (H == 256) {
+    dim3 grid256(L256_NC * ((B + L256_NB - 1) / L256_NB), 2);
+    bilstm256_cluster_kernel<<<grid256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld);
     ASB_CUDA(cudaGetLastError());
     return AS_OK;

@@ -271,8 +271,8 @@ def bilstm(xproj, whh_t, hidden, lens, out_dtype):
             h = torch.zeros(H)
             c = torch.zeros(H)
             W = whh_t[d].float()                                      # [H, 4H]
-            q16 = H == 128 and EMULATE_FP16_RECURRENCE
-            if q16:   # the H=128 kernel keeps W_hh and h as fp16 tensor-core operands (fp32 accumulate)
+            q16 = H in (128, 256) and EMULATE_FP16_RECURRENCE
+            if q16:   # the H=128/256 kernels keep W_hh and h as fp16 tensor-core operands (fp32 accumulate)
                 W = W.half().float()
             order = range(L) if d == 0 else range(L - 1, -1, -1)
             for t in order:

@@ -205,16 +205,16 @@ def test_conv_small_dwconv_pools():
         _close(out, ref, 1e-4, "gap")
 
 
+@pytest.mark.parametrize("B,T", [(5, 60), (16, 240), (19, 33)])
 @pytest.mark.parametrize("H", [128, 256])
-def test_bilstm(H):
+def test_bilstm(H, B, T):
     torch.manual_seed(10)
-    B, T = 5, 60
     xp = torch.randn(B, T, 8 * H)
     whh_t = torch.randn(2, H, 4 * H) / H ** 0.5
     lens = _lens(B, T)
     ref = sim.bilstm(xp, whh_t, H, lens, torch.float32)
     out = ops.bilstm(xp.to(DEV), whh_t.to(DEV), H, lens.to(DEV), torch.float32)
-    _close(out, ref, 2e-5 if H == 256 else 1e-3)   # H=128: fp16 tensor-core recurrence (rounding points differ)
+    _close(out, ref, 1e-3)   # fp16 tensor-core recurrence (rounding points differ from the model's)
     ref = sim.lstm_onestep(xp, H, torch.float32)
     out = ops.lstm_onestep(xp.to(DEV), H, torch.float32)
     _close(out, ref, 1e-5)

@@ -18,6 +18,7 @@
 // two epilogue warpgroups that drain the accumulator stages alternately (TMEM lane quadrant =
 // warp_idx % 4), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -46,6 +47,7 @@ struct ConvArgs {
   // fast-epilogue plan (host-computed): tensor kinds 0 absent / 1 launch 16-bit format / 2 fp32
   int fast, k_res1, k_res2, k_raw, k_act, act_simple;
   float act_slope_eff;
+  int halo_rows, pad_lo;   // narrow-channel variant: rows per plane of the halo tile, -min(tap_dt)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -248,6 +250,107 @@ __device__ __forceinline__ void store_fast(char* p, int kind, const float (&v)[1
 }
 
 // ---------------------------------------------------------------------------------------------
+// epilogue (shared by both kernels): two warpgroups alternate tiles; TMEM -> registers -> global
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool BF16>
+__device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint32_t tfull0,
+                                             uint32_t tempty0, int warp, int lane, int m_tiles,
+                                             int total_tiles) {
+  auto tfull_bar = [&](int i) { return tfull0 + 8u * i; };
+  auto tempty_bar = [&](int i) { return tempty0 + 8u * i; };
+    const int wg = (warp - 2) >> 2;  // 0 / 1 = accumulator stage this warpgroup drains
+  const int q = warp & 3;          // TMEM lane quadrant this warp may access
+  const int m = q * 32 + lane;     // tile row
+  const int it_ = m / a.tF, if_ = m - it_ * a.tF;
+  int lt = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    if ((lt & 1) != wg) continue;
+    int mt = tile % m_tiles;
+    const int n0 = (tile / m_tiles) * BN;
+    const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
+    const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
+    const int b = mt;
+    const int t = tt * a.tT + it_, f = ft * a.tF + if_;
+    const bool row_ok = (t < a.To) && (f < a.Fo);
+    bool masked = false;
+    if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
+    const long long row = ((long long)b * a.To + t) * a.Fo + f;
+
+    // per-tile constants of the fast path (byte pointers of this thread's row, kinds, slope)
+    const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
+    const bool fast = a.fast != 0;
+    const int k_r1 = a.k_res1, k_r2 = a.k_res2, k_raw = a.k_raw, k_act = a.k_act;
+    const char* p_r1 = k_r1 ? reinterpret_cast<const char*>(a.res1) + (row * a.res1_ld + n0) * (k_r1 == 1 ? 2 : 4) : nullptr;
+    const char* p_r2 = k_r2 ? reinterpret_cast<const char*>(a.res2) + (row * a.res2_ld + n0) * (k_r2 == 1 ? 2 : 4) : nullptr;
+    char* p_raw = k_raw ? reinterpret_cast<char*>(a.y_raw) + (row * a.y_raw_ld + n0) * (k_raw == 1 ? 2 : 4) : nullptr;
+    char* p_act = k_act ? reinterpret_cast<char*>(a.y_act) + (row * a.y_act_ld + n0) * (k_act == 1 ? 2 : 4) : nullptr;
+    const float scale = masked ? 0.f : a.out_scale;   // masked rows become exact zeros (res are finite)
+    const float aslope = a.act_slope_eff;
+
+    mbar_wait(tfull_bar(wg), ((uint32_t)lt >> 1) & 1u);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (c0 >= ncols) break;  // warp-uniform
+      uint32_t r[16];
+      tc_ld16(tacc + uint32_t(c0), r);
+      tc_wait_ld();
+      if (!row_ok) continue;
+      const int co = n0 + c0;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      if (fast && c0 + 16 <= ncols) {
+        if (a.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + co) + i);
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+          }
+        }
+        if (k_r1 && !masked) add_res_fast<BF16>(p_r1 + c0 * (k_r1 == 1 ? 2 : 4), k_r1, v);
+        if (k_r2 && !masked) add_res_fast<BF16>(p_r2 + c0 * (k_r2 == 1 ? 2 : 4), k_r2, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= scale;
+        if (k_raw) store_fast<BF16>(p_raw + c0 * (k_raw == 1 ? 2 : 4), k_raw, v);
+        if (k_act) {
+          if (a.act_simple) {
+            // none / lrelu / relu / abs: act(v) = max(v, v * s) with s = 1 / slope / 0 / -1
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * aslope);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+          }
+          store_fast<BF16>(p_act + c0 * (k_act == 1 ? 2 : 4), k_act, v);
+        }
+      } else {
+        // generic path: partial chunks (Cout not a multiple of 16), unaligned or mixed-format tensors
+        const int nvalid = min(16, a.Cout - co);
+        if (a.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
+        }
+        if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid, false);
+        if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid, false);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
+        if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid, false);
+        if (a.y_act != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+          store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, false);
+        }
+      }
+    }
+    // all TMEM reads of this stage are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK, bool BF16>
@@ -350,97 +453,135 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: two warpgroups alternate tiles; TMEM -> registers -> global =====
-    const int wg = (warp - 2) >> 2;  // 0 / 1 = accumulator stage this warpgroup drains
-    const int q = warp & 3;          // TMEM lane quadrant this warp may access
-    const int m = q * 32 + lane;     // tile row
-    const int it_ = m / a.tF, if_ = m - it_ * a.tF;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      if ((lt & 1) != wg) continue;
-      int mt = tile % m_tiles;
-      const int n0 = (tile / m_tiles) * BN;
-      const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
-      const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
-      const int b = mt;
-      const int t = tt * a.tT + it_, f = ft * a.tF + if_;
-      const bool row_ok = (t < a.To) && (f < a.Fo);
-      bool masked = false;
-      if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
-      const long long row = ((long long)b * a.To + t) * a.Fo + f;
+    // ===== epilogue =====
+    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles);
+  }
 
-      // per-tile constants of the fast path (byte pointers of this thread's row, kinds, slope)
-      const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
-      const bool fast = a.fast != 0;
-      const int k_r1 = a.k_res1, k_r2 = a.k_res2, k_raw = a.k_raw, k_act = a.k_act;
-      const char* p_r1 = k_r1 ? reinterpret_cast<const char*>(a.res1) + (row * a.res1_ld + n0) * (k_r1 == 1 ? 2 : 4) : nullptr;
-      const char* p_r2 = k_r2 ? reinterpret_cast<const char*>(a.res2) + (row * a.res2_ld + n0) * (k_r2 == 1 ? 2 : 4) : nullptr;
-      char* p_raw = k_raw ? reinterpret_cast<char*>(a.y_raw) + (row * a.y_raw_ld + n0) * (k_raw == 1 ? 2 : 4) : nullptr;
-      char* p_act = k_act ? reinterpret_cast<char*>(a.y_act) + (row * a.y_act_ld + n0) * (k_act == 1 ? 2 : 4) : nullptr;
-      const float scale = masked ? 0.f : a.out_scale;   // masked rows become exact zeros (res are finite)
-      const float aslope = a.act_slope_eff;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
 
-      mbar_wait(tfull_bar(wg), ((uint32_t)lt >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        if (c0 >= ncols) break;  // warp-uniform
-        uint32_t r[16];
-        tc_ld16(tacc + uint32_t(c0), r);
-        tc_wait_ld();
-        if (!row_ok) continue;
-        const int co = n0 + c0;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (fast && c0 + 16 <= ncols) {
-          if (a.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + co) + i);
-              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-            }
-          }
-          if (k_r1 && !masked) add_res_fast<BF16>(p_r1 + c0 * (k_r1 == 1 ? 2 : 4), k_r1, v);
-          if (k_r2 && !masked) add_res_fast<BF16>(p_r2 + c0 * (k_r2 == 1 ? 2 : 4), k_r2, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= scale;
-          if (k_raw) store_fast<BF16>(p_raw + c0 * (k_raw == 1 ? 2 : 4), k_raw, v);
-          if (k_act) {
-            if (a.act_simple) {
-              // none / lrelu / relu / abs: act(v) = max(v, v * s) with s = 1 / slope / 0 / -1
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * aslope);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-            }
-            store_fast<BF16>(p_act + c0 * (k_act == 1 ? 2 : 4), k_act, v);
-          }
-        } else {
-          // generic path: partial chunks (Cout not a multiple of 16), unaligned or mixed-format tensors
-          const int nvalid = min(16, a.Cout - co);
-          if (a.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
-          }
-          if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid, false);
-          if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid, false);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
-          if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid, false);
-          if (a.y_act != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-            store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, false);
+
+// ---------------------------------------------------------------------------------------------
+// Narrow-channel 1-D variant (Cin, Cout <= 64: vocoder stages with 64 / 32 channels, 37 % of its
+// FLOPs but > 50 % of its time with the kernel above, which re-loads the activation tile once per
+// tap).  Here the activation tile is loaded ONCE per output tile with its halo
+// (128 + (k-1)*dil rows) and ALL taps' weights stay resident in shared memory for the CTA's life:
+// L2->smem traffic per tile drops from k*(A+W) to ~1.4*A.
+//
+// Layout: un-swizzled K-major "core matrix" planes.  One TMA box {8 ch, HRP rows, Cin/8 planes}
+// of a tensor map whose dimensions are ordered (8 channels, time, channel-block) lands in shared
+// memory as [plane][row][8 ch]: every 16-byte unit is one row of an 8x8 core matrix, 8 rows are
+// contiguous (128 B), so a tap is simply a start-address offset of `rows * 16` bytes in the UMMA
+// descriptor (LBO = plane stride, SBO = 128 B) — no swizzle phase to keep aligned.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes) {
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
+}
+
+template <int BN, bool BF16>
+__global__ void __launch_bounds__(CV_THREADS)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ ConvArgs a) {
+  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 127u) & ~127u;
+  const int S = a.stages;
+  const int KC = a.kchunks;                 // 8-channel planes
+  const int HRP = a.halo_rows;              // rows per plane of the A tile (multiple of 8)
+  const uint32_t a_bytes = (uint32_t)KC * HRP * 16;
+  const uint32_t w_tap_bytes = (uint32_t)KC * BN * 16;
+  const uint32_t w_base = smem_base + S * a_bytes;
+  const uint32_t bar_base = (w_base + a.ntaps * w_tap_bytes + 7u) & ~7u;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
+  const uint32_t w_bar = bar_base + 8u * (2 * S + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = a.B * a.n_ttiles;
+  const int total_tiles = m_tiles;          // single N tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: weights once, then one halo tile per output tile =====
+      mbar_expect_tx(w_bar, a.ntaps * w_tap_bytes);
+      for (int tap = 0; tap < a.ntaps; ++tap)
+        tma_load_4d(w_base + tap * w_tap_bytes, &tmW, w_bar, 0, tap * a.CoutP, 0, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tt = tile % a.n_ttiles, b = tile / a.n_ttiles;
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), a_bytes);
+        tma_load_4d(smem_base + s * a_bytes, &tmA, full_bar(s), 0, tt * 128 - a.pad_lo, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      mbar_wait(w_bar, 0);
+      int lt = 0;
+      const int ksteps = KC / 2;             // 16 channels per MMA
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const int s = lt % S;
+        const uint32_t ph = (lt / S) & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t sa = smem_base + s * a_bytes;
+        uint32_t first = 0;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+          const uint32_t arow = sa + (uint32_t)(a.pad_lo + a.tap_dt[tap]) * 16u;
+          const uint32_t wtap = w_base + tap * w_tap_bytes;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t da = make_desc_noswz(arow + (uint32_t)(2 * j * HRP) * 16u, (uint32_t)HRP * 16u);
+            const uint64_t db = make_desc_noswz(wtap + (uint32_t)(2 * j * BN) * 16u, (uint32_t)BN * 16u);
+            tc_mma_f16(tacc, da, db, a.idesc, first);
+            first = 1u;
           }
         }
+        tc_commit(empty_bar(s));
+        tc_commit(tfull_bar(acc));
       }
-      // all TMEM reads of this stage are complete (tcgen05.wait::ld above): hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
     }
+  } else {
+    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles);
   }
 
   tc_fence_before();
@@ -522,6 +663,72 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs&
   conv_igemm_kernel<BN, BK, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
+}
+
+template <int BN, bool BF16>
+static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, cudaStream_t st) {
+  const int KC = p->Cin / 8;
+  int lo = 0, hi = 0;
+  for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
+  const int HRP = (128 + hi - lo + 7) / 8 * 8;
+  a.kchunks = KC; a.halo_rows = HRP; a.pad_lo = -lo;
+  a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;
+  const size_t a_bytes = (size_t)KC * HRP * 16, w_bytes = (size_t)p->ntaps * KC * BN * 16;
+  int stages = 4;
+  while (stages > 2 && stages * a_bytes + w_bytes > 190 * 1024) --stages;
+  a.stages = stages;
+  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + 256;
+  const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmA, tmW;
+  {
+    // dims ordered (8 channels, time, channel block, batch): smem gets [plane][row][8ch]
+    cuuint64_t dims[4] = {8, (cuuint64_t)p->T, (cuuint64_t)KC, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, 16, (cuuint64_t)p->x_ld * 2 * p->T};
+    cuuint32_t box[4] = {8, (cuuint32_t)HRP, (cuuint32_t)KC, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(p->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo A) failed: %d", (int)r);
+  }
+  {
+    // packed weights [ntaps*CoutP rows][CinP]: (8 ci, rows, ci block, 1) -> [plane][co][8ci] per tap
+    cuuint64_t dims[4] = {8, (cuuint64_t)p->ntaps * p->CoutP, (cuuint64_t)KC, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)p->CinP * 2, 16, (cuuint64_t)p->CinP * 2 * p->ntaps * p->CoutP};
+    cuuint32_t box[4] = {8, (cuuint32_t)BN, (cuuint32_t)KC, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmW, dt, 4, const_cast<void*>(p->w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo W) failed: %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = p->B * a.n_ttiles;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > total_tiles) grid = total_tiles;
+  conv_halo_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
+static bool halo_eligible(const as_conv_params* p, int bn) {
+  if (p->F != 1 || p->Fo != 1 || p->To != p->T) return false;
+  // measured on B200 (tools/prof_conv.py): a win for 32 channels (-15 %), a loss for 64 (the wider
+  // kernel keeps two CTAs per SM there, which hides the epilogue's residual-load latency better)
+  if (p->Cin % 16 != 0 || p->Cin > 32 || p->CinP != p->Cin || bn > 64 || p->CoutP != bn) return false;
+  int lo = 0, hi = 0;
+  for (int j = 0; j < p->ntaps; ++j) {
+    if (p->tap_df[j] != 0) return false;
+    lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi;
+  }
+  if (128 + hi - lo > 248) return false;
+  const size_t w_bytes = (size_t)p->ntaps * (p->Cin / 8) * bn * 16;
+  return w_bytes <= 100 * 1024;
 }
 
 static int esize(int dtype) { return dtype == AS_F32 ? 4 : 2; }
@@ -642,8 +849,15 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
     ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
 
-  const int total_tiles = p->B * a.n_ttiles * a.n_ftiles * (p->CoutP / bn);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool no_halo = getenv("ASB_NO_HALO") != nullptr;
+  if (!no_halo && halo_eligible(p, bn)) {
+    const bool bf = p->x_dtype == AS_BF16;
+#define HALO_CASE(BN_) if (bn == BN_) return bf ? launch_halo<BN_, true>(p, a, enc, st) : launch_halo<BN_, false>(p, a, enc, st);
+    HALO_CASE(16) HALO_CASE(32) HALO_CASE(64)
+#undef HALO_CASE
+  }
+  const int total_tiles = p->B * a.n_ttiles * a.n_ftiles * (p->CoutP / bn);
 #define CV_CASE(BN_, BK_)                                                                    \
   if (bn == BN_ && bk == BK_)                                                                \
     return p->x_dtype == AS_BF16 ? launch_conv<BN_, BK_, true>(tmA, tmW, a, total_tiles, st) \

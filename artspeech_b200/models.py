@@ -338,10 +338,7 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
         rd = self.res_dtype
         need16 = rd != dt
         xs, _, _ = run_adain_block(p["shared"], a16, gbs[0], gbs[1], lens, dt, res_dtype=rd)
-        outs = []
-        g = 2
-        lens2 = lens
-        for name in ("F0", "N", "EMA"):
+        def branch(name, g):
             bp = p["br"][name]
             y, y16, l = xs, None, lens
             for j, blk in enumerate(bp["blocks"]):
@@ -349,12 +346,15 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
                 # their input; the last block's 16-bit copy is the LSTM projection's operand
                 y, y16, l = run_adain_block(blk, y, gbs[g + 2 * j], gbs[g + 2 * j + 1], l, dt, res_dtype=rd,
                                             x16=y16, out16=dt if need16 else None)
-            g += 6
             xproj, _ = ops.conv(y16 if need16 else y, bp["lstm_proj"], raw=torch.float32)
             h16 = ops.bilstm(xproj, bp["whh_t"], self.d_hid // 4, l, dt)
             o, _ = ops.conv(h16, bp["out"], raw=torch.float32, lens=l)
-            outs.append(o)
-            lens2 = l
+            return o, l
+        # the three predictor branches are independent (models.py:603-619): concurrent streams
+        res = ops.run_concurrently([lambda n=n_, g=g_: branch(n, g) for n_, g_ in (("F0", 2), ("N", 8), ("EMA", 14))],
+                                   a16.device)
+        outs = [r[0] for r in res]
+        lens2 = res[0][1]
         return outs[0], outs[1], outs[2], lens2
 
     @torch.no_grad()
@@ -523,11 +523,14 @@ class ArtsSpeech(nn.Module):
         B, Tt = texts.shape
         lens_t = _i32(input_lengths, dev)
 
-        T_en = self.text_encoder(texts, input_lengths)                                   # [B,Tt,512] fp32 (:357)
-        A_en = self.arts_encoder(texts, input_lengths)                                   # (:358)
         hm = host_meta or {}
-        f0_ext, n_ext, ema_ext, style = self.style_encoder(mels, mel_input_length, "second", self.distribution,
-                                                           host_lengths=hm.get("mel_lens"))
+        # the two text encoders and the style encoder are independent (:357-359): run them on
+        # concurrent streams (each is a latency-bound chain of small kernels)
+        T_en, A_en, (f0_ext, n_ext, ema_ext, style) = ops.run_concurrently([
+            lambda: self.text_encoder(texts, input_lengths),                             # [B,Tt,512] fp32 (:357)
+            lambda: self.arts_encoder(texts, input_lengths),                             # (:358)
+            lambda: self.style_encoder(mels, mel_input_length, "second", self.distribution,
+                                       host_lengths=hm.get("mel_lens"))], dev)           # (:359)
         if durations is None:
             duration = self.durationPredictor(texts, ema_ext, input_lengths, mel_input_length,
                                               host_mel_lengths=hm.get("mel_lens"))                # (:360)

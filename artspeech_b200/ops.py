@@ -458,3 +458,48 @@ def to_channels_first(src, out_dtype, lens=None, sub=None, mul=None):
     _run("as_transpose_cast", src, src.data_ptr(), dtype_code(src.dtype), out.data_ptr(), dtype_code(out_dtype),
          B, C_, T, _rows_ld(src, "tcf.src"), 0, _p(sub), _p(mul), _p(_i32(lens, "to_cf")))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# stream-level concurrency for independent sub-graphs (capturable in a CUDA graph)
+# --------------------------------------------------------------------------------------------
+_side_streams = {}
+
+
+def run_concurrently(fns, device):
+    """Run the callables ``fns`` on separate CUDA streams forked from / joined to the current one
+    and return their results.  Independent branches of the model (the three encoders, the three
+    predictor branches) are latency-bound chains of small kernels: overlapping them fills the SMs.
+    On CPU tensors (host-logic tests) the callables simply run in order."""
+    if device is None or torch.device(device).type != "cuda" or len(fns) <= 1:
+        return [f() for f in fns]
+    dev = torch.device(device)
+    main = torch.cuda.current_stream(dev)
+    pool = _side_streams.setdefault((dev.index, len(fns)), [torch.cuda.Stream(device=dev) for _ in fns])
+    fork = torch.cuda.Event()
+    fork.record(main)
+    results, joins = [], []
+    for f, st in zip(fns, pool):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            r = f()
+            ev = torch.cuda.Event()
+            ev.record(st)
+        results.append(r)
+        joins.append(ev)
+    for ev in joins:
+        main.wait_event(ev)
+
+    def _mark(o):
+        if torch.is_tensor(o):
+            if o.is_cuda:
+                o.record_stream(main)
+        elif isinstance(o, (tuple, list)):
+            for x in o:
+                _mark(x)
+        elif isinstance(o, dict):
+            for x in o.values():
+                _mark(x)
+    for r in results:
+        _mark(r)
+    return results

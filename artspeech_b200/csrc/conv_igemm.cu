@@ -47,7 +47,8 @@ struct ConvArgs {
   // fast-epilogue plan (host-computed): tensor kinds 0 absent / 1 launch 16-bit format / 2 fp32
   int fast, k_res1, k_res2, k_raw, k_act, act_simple;
   float act_slope_eff;
-  int halo_rows, pad_lo;   // narrow-channel variant: rows per plane of the halo tile, -min(tap_dt)
+  int halo_rows, pad_lo;   // halo variants: rows of the halo tile, -min(tap_dt)
+  int halo_baseoff;        // swizzled halo: put (row & 7) into the descriptor's base-offset field
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -255,7 +256,12 @@ __device__ __forceinline__ void store_fast(char* p, int kind, const float (&v)[1
 template <int BN, bool BF16>
 __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint32_t tfull0,
                                              uint32_t tempty0, int warp, int lane, int m_tiles,
-                                             int total_tiles) {
+                                             int total_tiles, const float* bias_s) {
+  // 16-bit residual rows are fetched into registers BEFORE the accumulator wait (ncu: the epilogue
+  // warps were stalled on these loads, long_scoreboard ~12 cycles/issue): up to 128 channels/row.
+  // BN = 256 runs one CTA per SM (<= 204 regs/thread): 128 channels; narrower tiles run two CTAs
+  // per SM (<= 102 regs/thread): 64 channels.
+  constexpr int NPRE = (BN >= 256 ? 128 : (BN < 64 ? BN : 64)) / 8;   // uint4 registers of residual prefetch
   auto tfull_bar = [&](int i) { return tfull0 + 8u * i; };
   auto tempty_bar = [&](int i) { return tempty0 + 8u * i; };
     const int wg = (warp - 2) >> 2;  // 0 / 1 = accumulator stage this warpgroup drains
@@ -286,11 +292,21 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     char* p_act = k_act ? reinterpret_cast<char*>(a.y_act) + (row * a.y_act_ld + n0) * (k_act == 1 ? 2 : 4) : nullptr;
     const float scale = masked ? 0.f : a.out_scale;   // masked rows become exact zeros (res are finite)
     const float aslope = a.act_slope_eff;
+    const float* bias_t = bias_s + n0;
+    const bool pre_ok = fast && k_r1 == 1 && row_ok && !masked;
+    uint4 pre[NPRE];
+    if (pre_ok) {
+#pragma unroll
+      for (int i = 0; i < NPRE; ++i)
+        if (i * 8 + 8 <= ncols) pre[i] = __ldg(reinterpret_cast<const uint4*>(p_r1) + i);
+    }
 
     mbar_wait(tfull_bar(wg), ((uint32_t)lt >> 1) & 1u);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+#pragma unroll
+    for (int cc = 0; cc < BN / 16; ++cc) {
+      const int c0 = cc * 16;
       if (c0 >= ncols) break;  // warp-uniform
       uint32_t r[16];
       tc_ld16(tacc + uint32_t(c0), r);
@@ -301,14 +317,20 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
       if (fast && c0 + 16 <= ncols) {
-        if (a.bias != nullptr) {
+        {   // bias staged in shared memory once per CTA (zeros when the layer has none)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + co) + i);
+            const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + 4 * i);
             v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
           }
         }
-        if (k_r1 && !masked) add_res_fast<BF16>(p_r1 + c0 * (k_r1 == 1 ? 2 : 4), k_r1, v);
+        if (pre_ok && 2 * cc + 1 < NPRE) {
+          const uint4 t0 = pre[(2 * cc) < NPRE ? 2 * cc : 0], t1 = pre[(2 * cc + 1) < NPRE ? 2 * cc + 1 : 0];
+          unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+          unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+          unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+          unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+        } else if (k_r1 && !masked) add_res_fast<BF16>(p_r1 + c0 * (k_r1 == 1 ? 2 : 4), k_r1, v);
         if (k_r2 && !masked) add_res_fast<BF16>(p_r2 + c0 * (k_r2 == 1 ? 2 : 4), k_r2, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= scale;
@@ -354,7 +376,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK, bool BF16>
-__global__ void __launch_bounds__(CV_THREADS)
+__global__ void __launch_bounds__(CV_THREADS, (BN >= 256 ? 1 : 2))
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ ConvArgs a) {
   constexpr int A_BYTES = 128 * BK * 2;
@@ -371,6 +393,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
+  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -454,7 +478,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===== epilogue =====
-    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles);
+    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
   }
 
   tc_fence_before();
@@ -487,7 +511,7 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo
 }
 
 template <int BN, bool BF16>
-__global__ void __launch_bounds__(CV_THREADS)
+__global__ void __launch_bounds__(CV_THREADS, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ ConvArgs a) {
   constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
@@ -506,6 +530,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
   const uint32_t w_bar = bar_base + 8u * (2 * S + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
+  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -581,7 +607,132 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles);
+    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Swizzled halo variant for 64 / 128 input channels (vocoder stages 1-2).  ncu showed the per-tap
+// kernel is bound by L2->SM bandwidth there (lts ~52 %, 44 B/clk/SM: the LTS cap): each tap re-loads
+// the activation tile and every tile re-streams the weights.  Here the activation tile (with halo)
+// is loaded once per output tile as 64-channel chunks in the standard 128B-swizzled K-major layout
+// (full-width 128 B TMA rows) and all taps' weights are resident in shared memory.  A tap is a
+// start-address offset of r*128 B into the swizzled tile.  Measured on B200: the UMMA swizzle is a
+// function of the absolute shared-memory address bits (like TMA's), so an unaligned start row
+// needs NO base-offset in the descriptor (setting bits 49..51 to r & 7 gives wrong results;
+// tests/test_kernels_gpu.py covers row offsets 1..25).
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool BF16>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ ConvArgs a) {
+  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int S = a.stages;
+  const int KCH = a.kchunks;                // 64-channel chunks
+  const int HRP = a.halo_rows;              // rows of the halo tile (multiple of 8)
+  const uint32_t chunk_bytes = (uint32_t)HRP * 128u;
+  const uint32_t a_bytes = (uint32_t)KCH * chunk_bytes;
+  const uint32_t w_blk = (uint32_t)BN * 128u;                       // one (tap, chunk) weight block
+  const uint32_t w_base = smem_base + S * a_bytes;
+  const uint32_t bar_base = w_base + a.ntaps * KCH * w_blk;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
+  const uint32_t w_bar = bar_base + 8u * (2 * S + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
+  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = a.B * a.n_ttiles;
+  const int total_tiles = m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, a.ntaps * KCH * w_blk);
+      for (int tap = 0; tap < a.ntaps; ++tap)
+        for (int c = 0; c < KCH; ++c)
+          tma_load_2d(w_base + (tap * KCH + c) * w_blk, &tmW, w_bar, c * 64, tap * a.CoutP);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tt = tile % a.n_ttiles, b = tile / a.n_ttiles;
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), a_bytes);
+        for (int c = 0; c < KCH; ++c)
+          tma_load_4d(smem_base + s * a_bytes + c * chunk_bytes, &tmA, full_bar(s), c * 64, 0, tt * 128 - a.pad_lo, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(w_bar, 0);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const int s = lt % S;
+        const uint32_t ph = (lt / S) & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t sa = smem_base + s * a_bytes;
+        uint32_t first = 0;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+          const uint32_t r = (uint32_t)(a.pad_lo + a.tap_dt[tap]);
+          const uint64_t boff = a.halo_baseoff ? (uint64_t(r & 7u) << 49) : 0ull;
+          for (int c = 0; c < KCH; ++c) {
+            const uint64_t da = make_smem_desc<64>(sa + c * chunk_bytes + r * 128u) | boff;
+            const uint64_t db = make_smem_desc<64>(w_base + (tap * KCH + c) * w_blk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_f16(tacc, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc, first);
+              first = 1u;
+            }
+          }
+        }
+        tc_commit(empty_bar(s));
+        tc_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
   }
 
   tc_fence_before();
@@ -646,16 +797,16 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs&
   // BN = 256 needs all 512 TMEM columns (two accumulator stages): one CTA per SM with a deep ring.
   // Narrower tiles run two CTAs per SM (TMEM 2*BN <= 256 columns each, ~100 KB of ring each).
   const int ctas_per_sm = BN >= 256 ? 1 : 2;
-  const int budget = (BN >= 256 ? 196 : 98) * 1024;
+  const int budget = (BN >= 256 ? 208 : 104) * 1024 - a.CoutP * 4;   // ring + bias tile within 227 KB / SM
   int stages = budget / STAGE_BYTES;
   if (stages > 10) stages = 10;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 5) + 1024;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, BF16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int grid = num_sms() * ctas_per_sm;
@@ -677,7 +828,7 @@ static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, 
   int stages = 4;
   while (stages > 2 && stages * a_bytes + w_bytes > 190 * 1024) --stages;
   a.stages = stages;
-  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + 256;
+  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 256 + 16;
   const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmW;
   {
@@ -702,7 +853,7 @@ static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ASB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int total_tiles = p->B * a.n_ttiles;
@@ -714,6 +865,71 @@ static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, 
   conv_halo_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
+}
+
+template <int BN, bool BF16>
+static int launch_halo_sw(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, cudaStream_t st) {
+  const int KCH = p->Cin / 64;
+  int lo = 0, hi = 0;
+  for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
+  const int HRP = (128 + hi - lo + 7) / 8 * 8;
+  a.kchunks = KCH; a.halo_rows = HRP; a.pad_lo = -lo;
+  static const int baseoff_mode = getenv("ASB_HALO_BASEOFF") ? atoi(getenv("ASB_HALO_BASEOFF")) : 0;
+  a.halo_baseoff = baseoff_mode;
+  a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;
+  const size_t a_bytes = (size_t)KCH * HRP * 128, w_bytes = (size_t)p->ntaps * KCH * BN * 128;
+  int stages = 4;
+  while (stages > 2 && stages * a_bytes + w_bytes > 200 * 1024) --stages;
+  a.stages = stages;
+  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16;
+  const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmA, tmW;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p->Cin, 1, (cuuint64_t)p->T, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->T};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)HRP, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(p->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw A) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p->CinP, (cuuint64_t)p->ntaps * p->CoutP};
+    cuuint64_t strides[1] = {(cuuint64_t)p->CinP * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmW, dt, 2, const_cast<void*>(p->w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw W) failed: %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASB_CUDA(cudaFuncSetAttribute(conv_halo_sw_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = p->B * a.n_ttiles;
+  int per_sm = (int)((226 * 1024) / (smem + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > total_tiles) grid = total_tiles;
+  conv_halo_sw_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
+static bool halo_sw_eligible(const as_conv_params* p, int bn) {
+  if (p->F != 1 || p->Fo != 1 || p->To != p->T) return false;
+  if (p->Cin % 64 != 0 || p->Cin > 128 || p->CinP != p->Cin || bn > 128 || p->CoutP != bn) return false;
+  int lo = 0, hi = 0;
+  for (int j = 0; j < p->ntaps; ++j) {
+    if (p->tap_df[j] != 0) return false;
+    lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi;
+  }
+  if (128 + hi - lo > 248) return false;
+  const size_t HRP = (128 + hi - lo + 7) / 8 * 8;
+  const size_t a_bytes = (size_t)(p->Cin / 64) * HRP * 128, w_bytes = (size_t)p->ntaps * (p->Cin / 64) * bn * 128;
+  return 2 * a_bytes + w_bytes + 16 * 1024 <= 200 * 1024;
 }
 
 static bool halo_eligible(const as_conv_params* p, int bn) {
@@ -851,6 +1067,13 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool no_halo = getenv("ASB_NO_HALO") != nullptr;
+  static const bool no_halo_sw = getenv("ASB_NO_HALO_SW") != nullptr;
+  if (!no_halo && !no_halo_sw && halo_sw_eligible(p, bn)) {
+    const bool bf = p->x_dtype == AS_BF16;
+#define HALOSW_CASE(BN_) if (bn == BN_) return bf ? launch_halo_sw<BN_, true>(p, a, enc, st) : launch_halo_sw<BN_, false>(p, a, enc, st);
+    HALOSW_CASE(16) HALOSW_CASE(32) HALOSW_CASE(64) HALOSW_CASE(128)
+#undef HALOSW_CASE
+  }
   if (!no_halo && halo_eligible(p, bn)) {
     const bool bf = p->x_dtype == AS_BF16;
 #define HALO_CASE(BN_) if (bn == BN_) return bf ? launch_halo<BN_, true>(p, a, enc, st) : launch_halo<BN_, false>(p, a, enc, st);

@@ -22,7 +22,6 @@
 
 namespace asb {
 
-constexpr int MAS_THREADS = 128;
 constexpr float MAS_NEG = -1e32f;
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
@@ -31,19 +30,27 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n"); }
 
+// Multi-warp wavefront: the rows are split over NW warps (32*R consecutive rows per warp, R rows per
+// lane).  Warp w can sweep a block of `cw` columns as soon as warp w-1 has swept the same block (it
+// needs that warp's last row, one column back), so at pipeline step tau warp w processes block
+// tau - w: NW blocks are in flight, one __syncthreads per step.  Inside a warp the diagonal operand
+// is a register (R > 1) or one __shfl_up_sync; across warps it travels through a tiny shared ring
+// (`bnd`) that the consumer pre-loads into registers per block.
 template <int R>
-__global__ void __launch_bounds__(MAS_THREADS)
+__global__ void __launch_bounds__(256)
 mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
            const int32_t* __restrict__ y_len, float* __restrict__ path, int Tx, int Ty,
-           int tie_move, uint32_t* __restrict__ dir_ws, int dir_in_smem, int cw) {
-  constexpr int ROWS = 32 * R;     // rows covered by warp 0
-  constexpr int PX = ROWS + 1;     // odd pitch of the transposed [col][row] tile
+           int tie_move, uint32_t* __restrict__ dir_ws, int dir_in_smem, int cw, int NW) {
+  constexpr int WR = 32 * R;       // rows per warp
+  constexpr int PX = WR + 1;       // odd pitch of a warp's transposed [col][row] sub-tile
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);                 // [2][cw][PX]
-  uint32_t* dir_s = reinterpret_cast<uint32_t*>(tile + 2 * cw * PX);  // [ROWS][W] if in smem
+  const int ROWS = WR * NW;
+  float* tile = reinterpret_cast<float*>(smem_raw);                     // [2][NW][cw][PX]
+  float* bnd = tile + 2 * NW * cw * PX;                                 // [NW][2][32] last-row values
+  uint32_t* dir_s = reinterpret_cast<uint32_t*>(bnd + NW * 2 * 32);     // [ROWS][W] if in smem
 
   const int b = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   int xl = x_len[b], yl = y_len[b];
   xl = min(max(xl, 0), Tx);
@@ -53,46 +60,51 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
   float* pb = path + (size_t)b * Tx * Ty;
   uint32_t* dirs = dir_in_smem ? dir_s : (dir_ws + (size_t)b * ROWS * W);
 
-  const int nwords = (yl + 31) >> 5;     // direction words actually used per row
-  const int nsub = (yl + cw - 1) / cw;   // column sub-chunks of cw columns (cw in {32,16,8})
+  const int nwords = (yl + 31) >> 5;
+  const int nblk = (yl + cw - 1) / cw;          // column blocks
+  const int nsteps = nblk > 0 ? nblk + NW - 1 : 0;
 
-  // ---- zero-fill bookkeeping for warps 1..3 (whole item, spread over the sub-chunks) ----
   const size_t total = (size_t)Tx * Ty;
+  if (nblk == 0 || xl == 0) {
+    // empty item (x_len == 0 or y_len == 0): the path is all zeros
+    for (size_t i = tid; i < total; i += nthr) pb[i] = 0.f;
+    return;
+  }
+  // zero-fill of `path`, spread over the pipeline steps (all threads; pure stores)
   const bool vec_ok = ((total & 3) == 0) && ((reinterpret_cast<uintptr_t>(pb) & 15) == 0);
-  const size_t nz = vec_ok ? (total >> 2) : total;  // units to write
-  const int zsteps = max(nsub, 1);
-  const size_t zper = (nz + zsteps - 1) / zsteps;
-
+  const size_t nz = vec_ok ? (total >> 2) : total;
+  const size_t zper = (nz + nsteps - 1) / nsteps;
   auto zero_slice = [&](int step) {
-    if (warp == 0) return;
     size_t lo = (size_t)step * zper, hi = min(nz, lo + zper);
     if (vec_ok) {
       float4* p4 = reinterpret_cast<float4*>(pb);
-      for (size_t i = lo + (tid - 32); i < hi; i += MAS_THREADS - 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (size_t i = lo + tid; i < hi; i += nthr) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      for (size_t i = lo + (tid - 32); i < hi; i += MAS_THREADS - 32) pb[i] = 0.f;
+      for (size_t i = lo + tid; i < hi; i += nthr) pb[i] = 0.f;
     }
   };
-
-  auto load_sub = [&](int sc) {
-    // rows [0, xl) x cols [cw*sc, cw*sc+cw) -> tile[sc&1][col][row]
-    float* dst = tile + (sc & 1) * cw * PX;
-    const int n = xl * cw;
-    for (int i = tid; i < n; i += MAS_THREADS) {
-      int col = i % cw, row = i / cw;
-      int y = sc * cw + col;
-      if (y < yl) cp_async4(smem_u32(dst + col * PX + row), vb + (size_t)row * Ty + y);
+  // stage the sub-tiles every warp needs at pipeline step `tau` (block tau - w for warp slot w)
+  auto load_step = [&](int tau) {
+    float* dst0 = tile + (size_t)(tau & 1) * NW * cw * PX;
+    for (int w = 0; w < NW; ++w) {
+      const int blk = tau - w;
+      if (blk < 0 || blk >= nblk) continue;
+      const int r0 = w * WR;
+      const int nrow = min(WR, xl - r0);
+      if (nrow <= 0) continue;
+      float* dst = dst0 + (size_t)w * cw * PX;
+      const int n = nrow * cw;
+      for (int i = tid; i < n; i += nthr) {
+        const int col = i % cw, row = i / cw;
+        const int y = blk * cw + col;
+        if (y < yl) cp_async4(smem_u32(dst + col * PX + row), vb + (size_t)(r0 + row) * Ty + y);
+      }
     }
     cp_async_commit();
   };
 
-  if (nsub == 0 || xl == 0) {
-    // empty item (x_len == 0 or y_len == 0): the path is all zeros
-    for (size_t i = tid; i < total; i += MAS_THREADS) pb[i] = 0.f;
-    return;
-  }
-
-  load_sub(0);
+  for (int i = tid; i < NW * 2 * 32; i += nthr) bnd[i] = MAS_NEG;
+  load_step(0);
   cp_async_wait_all();
   __syncthreads();
 
@@ -100,24 +112,35 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
   uint32_t bits[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) { q[r] = MAS_NEG; bits[r] = 0u; }
+  float carry = MAS_NEG;                       // boundary row value at the last column of my previous block
+  const int row0 = (warp * 32 + lane) * R;     // first row of this lane
+  const bool warp_active = warp * WR < xl;
 
-  for (int sc = 0; sc < nsub; ++sc) {
-    if (sc + 1 < nsub) load_sub(sc + 1);
-    zero_slice(sc);
-    if (warp == 0) {
-      const float* src = tile + (sc & 1) * cw * PX + lane * R;
-      const int ncol = min(cw, yl - sc * cw);
+  for (int tau = 0; tau < nsteps; ++tau) {
+    if (tau + 1 < nsteps) load_step(tau + 1);
+    zero_slice(tau);
+    const int blk = tau - warp;
+    if (warp_active && blk >= 0 && blk < nblk) {
+      const float* src = tile + ((size_t)(tau & 1) * NW + warp) * cw * PX + lane * R;
+      // boundary operands from the previous warp for this block's columns (lane c holds column c)
+      float bv = MAS_NEG;
+      if (warp > 0 && lane < cw) bv = bnd[((warp - 1) * 2 + (blk & 1)) * 32 + lane];
+      float* my_bnd = bnd + (warp * 2 + (blk & 1)) * 32;
+      const int ncol = min(cw, yl - blk * cw);
       for (int col = 0; col < ncol; ++col) {
         const float* vc = src + col * PX;
-        const int y = sc * cw + col;
+        const int y = blk * cw + col;
         if (y == 0) {
           // first column: only (0,0) is reachable (S_monotonic_align.py:23 / :68)
 #pragma unroll
           for (int r = 0; r < R; ++r) q[r] = MAS_NEG;
-          if (lane == 0) q[0] = vc[0];
+          if (row0 == 0) q[0] = vc[0];
         } else {
           float up = __shfl_up_sync(0xffffffffu, q[R - 1], 1);
-          if (lane == 0) up = MAS_NEG;  // row -1 (S_monotonic_align.py:28 / :73)
+          // lane 0: row above belongs to the previous warp (column y-1): this block's column col-1,
+          // or the carried last column of the previous block; warp 0 has row -1 (:28 / :73)
+          const float prevw = __shfl_sync(0xffffffffu, bv, (col + 31) & 31);
+          if (lane == 0) up = (warp == 0) ? MAS_NEG : (col == 0 ? carry : prevw);
           const int sh = y & 31;
 #pragma unroll
           for (int r = R - 1; r >= 0; --r) {
@@ -133,16 +156,18 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
             q[r] = vc[r] + best;
           }
         }
+        if (lane == 31) my_bnd[col] = q[R - 1];
         if ((y & 31) == 31 || y == yl - 1) {
-          // row 0 can never move to row -1 (maximum_path2 :91 `idx != 0`)
-          if (lane == 0) bits[0] = 0u;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            dirs[(size_t)(lane * R + r) * W + (y >> 5)] = bits[r];
+            // row 0 can never move to row -1 (maximum_path2 :91 `idx != 0`)
+            dirs[(size_t)(row0 + r) * W + (y >> 5)] = (row0 + r == 0) ? 0u : bits[r];
             bits[r] = 0u;
           }
         }
       }
+      // carry for my next block: the previous warp's value at the last column of this block
+      carry = __shfl_sync(0xffffffffu, bv, (cw - 1) & 31);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -175,49 +200,46 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
   }
 }
 
-template <int R>
-static int launch_mas(const float* value, const int32_t* x_len, const int32_t* y_len, float* path,
-                      int B, int Tx, int Ty, int tie_mode, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
-  constexpr int ROWS = 32 * R;
-  const int W = ((Ty + 31) / 32) | 1;
-  const size_t smem_cap = 200 * 1024;
-  int cw = 32;  // columns per staged sub-chunk: shrink until the double buffer fits
-  while (cw > 8 && (size_t)2 * cw * (ROWS + 1) * sizeof(float) > smem_cap / 2) cw >>= 1;
-  const size_t tile_bytes = (size_t)2 * cw * (ROWS + 1) * sizeof(float);
-  const size_t dir_bytes = (size_t)ROWS * W * sizeof(uint32_t);
-  int dir_in_smem = (tile_bytes + dir_bytes <= smem_cap) ? 1 : 0;
-  size_t smem = tile_bytes + (dir_in_smem ? dir_bytes : 0);
-  if (!dir_in_smem) {
-    ASB_REQUIRE(ws != nullptr && ws_bytes >= dir_bytes * (size_t)B, AS_ERR_WORKSPACE,
-                "as_mas_maximum_path: workspace too small (%zu < %zu)", ws_bytes,
-                dir_bytes * (size_t)B);
-  }
-  ASB_REQUIRE(tile_bytes <= smem_cap, AS_ERR_SHAPE, "as_mas_maximum_path: Tx=%d too large", Tx);
-  ASB_CUDA(cudaFuncSetAttribute(mas_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  mas_kernel<R><<<B, MAS_THREADS, smem, st>>>(value, x_len, y_len, path, Tx, Ty, tie_mode,
-                                               reinterpret_cast<uint32_t*>(ws), dir_in_smem, cw);
-  ASB_CUDA(cudaGetLastError());
-  return AS_OK;
+struct MasPlan { int R, NW, cw, W, dir_in_smem; size_t smem, dir_bytes_per_item; };
+
+static bool mas_plan(int Tx, int Ty, MasPlan& p) {
+  const int nwarp_rows = (Tx + 31) / 32;
+  p.NW = nwarp_rows < 8 ? (nwarp_rows < 1 ? 1 : nwarp_rows) : 8;
+  int need = (Tx + 32 * p.NW - 1) / (32 * p.NW);
+  static const int kR[] = {1, 3, 5};
+  p.R = -1;
+  for (int r : kR) if (r >= need) { p.R = r; break; }
+  if (p.R < 0) return false;
+  const int ROWS = 32 * p.R * p.NW;
+  p.W = ((Ty + 31) / 32) | 1;
+  const size_t cap = 200 * 1024;
+  p.cw = 32;
+  auto tile_bytes = [&](int cw) { return (size_t)2 * p.NW * cw * (32 * p.R + 1) * sizeof(float); };
+  while (p.cw > 8 && tile_bytes(p.cw) > cap / 2) p.cw >>= 1;
+  const size_t fixed = tile_bytes(p.cw) + (size_t)p.NW * 2 * 32 * sizeof(float);
+  p.dir_bytes_per_item = (size_t)ROWS * p.W * sizeof(uint32_t);
+  p.dir_in_smem = (fixed + p.dir_bytes_per_item <= cap) ? 1 : 0;
+  p.smem = fixed + (p.dir_in_smem ? p.dir_bytes_per_item : 0);
+  return fixed <= cap;
 }
 
-// rows per lane: odd (conflict-free shared reads) and one of the instantiated values
-static int mas_rows_per_lane(int Tx) {
-  static const int kR[] = {1, 3, 5, 7, 9, 13, 19, 25, 33};
-  const int need = (Tx + 31) / 32;
-  for (int r : kR) if (r >= need) return r;
-  return -1;
+template <int R>
+static int launch_mas(const MasPlan& p, const float* value, const int32_t* x_len, const int32_t* y_len,
+                      float* path, int B, int Tx, int Ty, int tie_mode, void* ws, cudaStream_t st) {
+  ASB_CUDA(cudaFuncSetAttribute(mas_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  mas_kernel<R><<<B, 32 * p.NW, p.smem, st>>>(value, x_len, y_len, path, Tx, Ty, tie_mode,
+                                              reinterpret_cast<uint32_t*>(ws), p.dir_in_smem, p.cw, p.NW);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
 }
 
 }  // namespace asb
 
 extern "C" size_t as_mas_workspace_bytes(int32_t B, int32_t Tx, int32_t Ty) {
   if (B <= 0 || Tx <= 0 || Ty <= 0) return 0;
-  int R = asb::mas_rows_per_lane(Tx);
-  if (R < 0) return 0;
-  size_t W = (size_t)((Ty + 31) / 32) | 1;
-  return (size_t)B * 32 * R * W * sizeof(uint32_t);
+  asb::MasPlan p;
+  if (!asb::mas_plan(Tx, Ty, p)) return 0;
+  return p.dir_in_smem ? 0 : (size_t)B * p.dir_bytes_per_item;
 }
 
 extern "C" int as_mas_maximum_path(const float* value, const int32_t* x_len, const int32_t* y_len,
@@ -231,15 +253,15 @@ extern "C" int as_mas_maximum_path(const float* value, const int32_t* x_len, con
   ASB_REQUIRE(tie_mode == 0 || tie_mode == 1, AS_ERR_SHAPE, "as_mas_maximum_path: tie_mode");
   int rc = check_arch();
   if (rc != AS_OK) return rc;
+  MasPlan p;
+  ASB_REQUIRE(mas_plan(Tx, Ty, p), AS_ERR_SHAPE, "as_mas_maximum_path: Tx=%d exceeds the supported maximum of 1280", Tx);
+  if (!p.dir_in_smem) {
+    ASB_REQUIRE(workspace != nullptr && workspace_bytes >= p.dir_bytes_per_item * (size_t)B, AS_ERR_WORKSPACE,
+                "as_mas_maximum_path: workspace too small (%zu < %zu)", workspace_bytes,
+                p.dir_bytes_per_item * (size_t)B);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int R = mas_rows_per_lane(Tx);
-#define MAS_CASE(RR)                                                                          \
-  if (R == RR)                                                                                \
-    return launch_mas<RR>(value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace,          \
-                          workspace_bytes, st);
-  MAS_CASE(1) MAS_CASE(3) MAS_CASE(5) MAS_CASE(7) MAS_CASE(9) MAS_CASE(13) MAS_CASE(19)
-  MAS_CASE(25) MAS_CASE(33)
-#undef MAS_CASE
-  set_error("as_mas_maximum_path: Tx=%d exceeds the supported maximum of 1056", Tx);
-  return AS_ERR_SHAPE;
+  if (p.R == 1) return launch_mas<1>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st);
+  if (p.R == 3) return launch_mas<3>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st);
+  return launch_mas<5>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st);
 }

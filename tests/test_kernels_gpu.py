@@ -30,7 +30,9 @@ def _lens(B, T, seed=0):
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 150, 512, 512, 5, 1), (2, 300, 128, 128, 7, 3), (1, 1000, 32, 32, 11, 5),
                                    (3, 77, 640, 1024, 3, 1), (2, 64, 80, 512, 7, 1), (2, 40, 88, 256, 1, 1),
-                                   (1, 500, 32, 1, 7, 1), (2, 130, 64, 192, 3, 1)])
+                                   (1, 500, 32, 1, 7, 1), (2, 130, 64, 192, 3, 1),
+                                   (2, 1000, 64, 64, 7, 3), (2, 500, 128, 128, 3, 1), (1, 700, 64, 64, 11, 5),
+                                   (2, 300, 64, 32, 3, 1), (3, 257, 128, 64, 3, 1)])
 def test_conv_igemm_1d(shape, dt):
     B, T, Cin, Cout, k, dil = shape
     torch.manual_seed(1)

@@ -48,6 +48,7 @@ struct ConvArgs {
   int fast, k_res1, k_res2, k_raw, k_act, act_simple;
   float act_slope_eff;
   int halo_rows, pad_lo;   // halo variants: rows of the halo tile, -min(tap_dt)
+  int epi_tma;             // 1: all-16-bit 1-D epilogue through shared memory + TMA
   int halo_baseoff;        // swizzled halo: put (row & 7) into the descriptor's base-offset field
 };
 
@@ -123,6 +124,38 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct EpiMaps { CUtensorMap r1, raw, act; };
+// per epilogue warp: 2 staging tiles of [32 rows][EPC channels]; EPC = 64 (128 B rows, 128B swizzle) or,
+// for tiles narrower than 64 channels, 32 (64 B rows, 64B swizzle)
+__host__ __device__ constexpr uint32_t epi_cols(int bn) { return bn >= 64 ? 64u : 32u; }
+__host__ __device__ constexpr uint32_t epi_warp_bytes(int bn) { return 2u * 32u * epi_cols(bn) * 2u; }
+__host__ __device__ constexpr uint32_t epi_bytes(int bn) { return 8u * epi_warp_bytes(bn) + 64u; }
 
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, =1) | [32,46) SBO>>4
@@ -373,11 +406,132 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA epilogue for the all-16-bit 1-D case (every vocoder conv).  ncu on the register->global
+// epilogue above: l1tex__data_pipe_lsu_wavefronts at 68 % of peak — a thread owns a row, so every
+// 16-byte access of a warp lands in a different 128-byte line (32 wavefronts per instruction).
+// Here each epilogue warp stages its 32 rows x 64 channels in a 128B-swizzled shared tile and moves
+// it with ONE bulk tensor copy per tensor: the residual arrives by TMA load (issued before the
+// accumulator wait), raw / activated outputs leave by TMA store.  Out-of-range rows / channels are
+// clipped by the TMA unit, so partial tiles need no special path.
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool BF16>
+__device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMaps& maps, uint32_t tmem_base,
+                                                 uint32_t tfull0, uint32_t tempty0, int warp, int lane, int m_tiles,
+                                                 int total_tiles, const float* bias_s, uint32_t epi_base) {
+  const int ew = warp - 2;                 // 0..7
+  const int wg = ew >> 2;
+  const int q = warp & 3;
+  constexpr uint32_t EPC = epi_cols(BN);                  // channels per staged group
+  constexpr uint32_t ROWB = EPC * 2u;                     // bytes per staged row (128 or 64)
+  constexpr uint32_t TILEB = 32u * ROWB;
+  constexpr int CPG = EPC / 16;                           // 16-channel chunks per group
+  const uint32_t bufA = epi_base + (uint32_t)ew * epi_warp_bytes(BN);   // residual in / raw out (in place)
+  const uint32_t bufB = bufA + TILEB;                                    // activated out
+  const uint32_t rbar = epi_base + 8u * epi_warp_bytes(BN) + 8u * ew;
+  const bool has_r1 = a.k_res1 == 1, has_raw = a.k_raw == 1, has_act = a.k_act == 1;
+  const uint32_t rowoff = (uint32_t)lane * ROWB;
+  // 16-byte unit swizzle of the TMA layout: 128B mode XORs with (row & 7), 64B mode with (row >> 1) & 3
+  const uint32_t sw = (EPC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+  uint32_t rphase = 0;
+  int lt = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    if ((lt & 1) != wg) continue;
+    const int mt = tile % m_tiles;
+    const int n0 = (tile / m_tiles) * BN;
+    const int tt = mt % a.n_ttiles, b = mt / a.n_ttiles;
+    const int t_base = tt * 128 + q * 32;
+    const int t = t_base + lane;
+    const bool masked = (a.lens != nullptr) && (t < a.To) && (t >= __ldg(a.lens + b));
+    const int ncols = min(BN, a.Cout - n0);
+    const int ngroups = (ncols + (int)EPC - 1) / (int)EPC;
+    const float scale = a.out_scale, aslope = a.act_slope_eff;
+
+    if (has_r1 && lane == 0 && ngroups > 0) {
+      bulk_wait_read0();                                   // previous stores have drained this buffer
+      mbar_expect_tx(rbar, TILEB);
+      tma_load_3d(bufA, &maps.r1, rbar, n0, t_base, b);
+    }
+    mbar_wait(tfull0 + 8u * wg, ((uint32_t)lt >> 1) & 1u);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
+    for (int g = 0; g < ngroups; ++g) {
+      if (has_r1) {
+        mbar_wait(rbar, rphase);
+        rphase ^= 1u;
+      } else {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int cc = 0; cc < CPG; ++cc) {
+        const int c0 = g * (int)EPC + cc * 16;
+        if (c0 < ncols) {   // warp-uniform
+          uint32_t r[16];
+          tc_ld16(tacc + uint32_t(c0), r);
+          tc_wait_ld();
+          float v[16];
+          const float* bt = bias_s + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = *reinterpret_cast<const float4*>(bt + 4 * i);
+            v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+          }
+          const uint32_t o0 = rowoff + (((uint32_t)(2 * cc) ^ sw) << 4), o1 = rowoff + (((uint32_t)(2 * cc + 1) ^ sw) << 4);
+          if (has_r1) {
+            const uint4 t0 = lds128(bufA + o0), t1 = lds128(bufA + o1);
+            unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+            unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+            unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+            unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * scale;
+          if (has_raw) {
+            sts128(bufA + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+            sts128(bufA + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+          }
+          if (has_act) {
+            if (a.act_simple) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * aslope);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
+            }
+            sts128(bufB + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+            sts128(bufB + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (has_raw) tma_store_3d(&maps.raw, bufA, n0 + g * (int)EPC, t_base, b);
+        if (has_act) tma_store_3d(&maps.act, bufB, n0 + g * (int)EPC, t_base, b);
+        bulk_commit();
+        if (has_r1 && g + 1 < ngroups) {
+          bulk_wait_read0();
+          mbar_expect_tx(rbar, TILEB);
+          tma_load_3d(bufA, &maps.r1, rbar, n0 + (g + 1) * (int)EPC, t_base, b);
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * wg) : "memory");
+  }
+  if (lane == 0) bulk_wait_all0();   // all stores complete before the CTA exits
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK, bool BF16>
 __global__ void __launch_bounds__(CV_THREADS, (BN >= 256 ? 1 : 2))
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ EpiMaps emaps,
                   const __grid_constant__ ConvArgs a) {
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int W_BYTES = BN * BK * 2;
@@ -395,6 +549,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
   for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
+  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -405,6 +560,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -478,7 +634,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===== epilogue =====
-    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
+    if (a.epi_tma)
+      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
+    else
+      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
   }
 
   tc_fence_before();
@@ -513,6 +672,7 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo
 template <int BN, bool BF16>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ EpiMaps emaps,
                  const __grid_constant__ ConvArgs a) {
   constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   extern __shared__ unsigned char smem_dyn[];
@@ -532,6 +692,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
   for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
+  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -542,6 +703,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     mbar_init(w_bar, 1);
+    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -607,7 +769,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
+    if (a.epi_tma)
+      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
+    else
+      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
   }
 
   tc_fence_before();
@@ -632,19 +797,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // needs NO base-offset in the descriptor (setting bits 49..51 to r & 7 gives wrong results;
 // tests/test_kernels_gpu.py covers row offsets 1..25).
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool BF16>
-__global__ void __launch_bounds__(CV_THREADS, 1)
+template <int BN, int BKC, bool BF16>
+__global__ void __launch_bounds__(CV_THREADS, 2)
 conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ EpiMaps emaps,
                     const __grid_constant__ ConvArgs a) {
   constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int S = a.stages;
-  const int KCH = a.kchunks;                // 64-channel chunks
+  constexpr uint32_t RB = BKC * 2u;          // bytes per row of a chunk: 128 (128B swizzle) or 64 (64B swizzle)
+  const int KCH = a.kchunks;                // BKC-channel chunks
   const int HRP = a.halo_rows;              // rows of the halo tile (multiple of 8)
-  const uint32_t chunk_bytes = (uint32_t)HRP * 128u;
+  const uint32_t chunk_bytes = (uint32_t)HRP * RB;
   const uint32_t a_bytes = (uint32_t)KCH * chunk_bytes;
-  const uint32_t w_blk = (uint32_t)BN * 128u;                       // one (tap, chunk) weight block
+  const uint32_t w_blk = (uint32_t)BN * RB;                         // one (tap, chunk) weight block
   const uint32_t w_base = smem_base + S * a_bytes;
   const uint32_t bar_base = w_base + a.ntaps * KCH * w_blk;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -655,6 +822,7 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
   for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
+  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -665,6 +833,7 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     mbar_init(w_bar, 1);
+    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -688,7 +857,7 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_expect_tx(w_bar, a.ntaps * KCH * w_blk);
       for (int tap = 0; tap < a.ntaps; ++tap)
         for (int c = 0; c < KCH; ++c)
-          tma_load_2d(w_base + (tap * KCH + c) * w_blk, &tmW, w_bar, c * 64, tap * a.CoutP);
+          tma_load_2d(w_base + (tap * KCH + c) * w_blk, &tmW, w_bar, c * BKC, tap * a.CoutP);
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int tt = tile % a.n_ttiles, b = tile / a.n_ttiles;
@@ -697,7 +866,7 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), a_bytes);
         for (int c = 0; c < KCH; ++c)
-          tma_load_4d(smem_base + s * a_bytes + c * chunk_bytes, &tmA, full_bar(s), c * 64, 0, tt * 128 - a.pad_lo, b);
+          tma_load_4d(smem_base + s * a_bytes + c * chunk_bytes, &tmA, full_bar(s), c * BKC, 0, tt * 128 - a.pad_lo, b);
       }
     }
   } else if (warp == 1) {
@@ -718,10 +887,10 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t r = (uint32_t)(a.pad_lo + a.tap_dt[tap]);
           const uint64_t boff = a.halo_baseoff ? (uint64_t(r & 7u) << 49) : 0ull;
           for (int c = 0; c < KCH; ++c) {
-            const uint64_t da = make_smem_desc<64>(sa + c * chunk_bytes + r * 128u) | boff;
-            const uint64_t db = make_smem_desc<64>(w_base + (tap * KCH + c) * w_blk);
+            const uint64_t da = make_smem_desc<BKC>(sa + c * chunk_bytes + r * RB) | boff;
+            const uint64_t db = make_smem_desc<BKC>(w_base + (tap * KCH + c) * w_blk);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < BKC / 16; ++k) {
               tc_mma_f16(tacc, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc, first);
               first = 1u;
             }
@@ -732,7 +901,10 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
+    if (a.epi_tma)
+      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
+    else
+      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
   }
 
   tc_fence_before();
@@ -791,18 +963,21 @@ static int num_sms() {
 }
 
 template <int BN, int BK, bool BF16>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs& a, int total_tiles,
-                       cudaStream_t st) {
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const EpiMaps& em, ConvArgs& a,
+                       int total_tiles, cudaStream_t st) {
   constexpr int STAGE_BYTES = 128 * BK * 2 + BN * BK * 2;
   // BN = 256 needs all 512 TMEM columns (two accumulator stages): one CTA per SM with a deep ring.
   // Narrower tiles run two CTAs per SM (TMEM 2*BN <= 256 columns each, ~100 KB of ring each).
-  const int ctas_per_sm = BN >= 256 ? 1 : 2;
-  const int budget = (BN >= 256 ? 208 : 104) * 1024 - a.CoutP * 4;   // ring + bias tile within 227 KB / SM
+  // The TMA epilogue needs 64 KB of staging per CTA: one CTA per SM with a deep ring instead of two.
+  const int ctas_per_sm = (BN >= 256 || a.epi_tma) ? 1 : 2;
+  const int budget = a.epi_tma ? (222 * 1024 - (int)epi_bytes(BN) - 2048 - a.CoutP * 4)
+                               : ((BN >= 256 ? 208 : 104) * 1024 - a.CoutP * 4);   // ring + bias within 227 KB / SM
   int stages = budget / STAGE_BYTES;
   if (stages > 10) stages = 10;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
+                      (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
   static bool attr_set = false;
   if (!attr_set) {
     ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, BF16>,
@@ -811,13 +986,13 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvArgs&
   }
   int grid = num_sms() * ctas_per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_igemm_kernel<BN, BK, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  conv_igemm_kernel<BN, BK, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
 
 template <int BN, bool BF16>
-static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, cudaStream_t st) {
+static int launch_halo(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeTiledFn enc, cudaStream_t st) {
   const int KC = p->Cin / 8;
   int lo = 0, hi = 0;
   for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
@@ -828,7 +1003,10 @@ static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, 
   int stages = 4;
   while (stages > 2 && stages * a_bytes + w_bytes > 190 * 1024) --stages;
   a.stages = stages;
-  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 256 + 16;
+  const size_t epi = a.epi_tma ? epi_bytes(BN) + 1024 : 0;
+  while (stages > 2 && stages * a_bytes + w_bytes + epi > 208 * 1024) --stages;
+  a.stages = stages;
+  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 256 + 16 + epi;
   const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmW;
   {
@@ -862,14 +1040,14 @@ static int launch_halo(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, 
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_halo_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  conv_halo_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
 
-template <int BN, bool BF16>
-static int launch_halo_sw(const as_conv_params* p, ConvArgs& a, EncodeTiledFn enc, cudaStream_t st) {
-  const int KCH = p->Cin / 64;
+template <int BN, int BKC, bool BF16>
+static int launch_halo_sw(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeTiledFn enc, cudaStream_t st) {
+  const int KCH = p->Cin / BKC;
   int lo = 0, hi = 0;
   for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
   const int HRP = (128 + hi - lo + 7) / 8 * 8;
@@ -877,34 +1055,40 @@ static int launch_halo_sw(const as_conv_params* p, ConvArgs& a, EncodeTiledFn en
   static const int baseoff_mode = getenv("ASB_HALO_BASEOFF") ? atoi(getenv("ASB_HALO_BASEOFF")) : 0;
   a.halo_baseoff = baseoff_mode;
   a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;
-  const size_t a_bytes = (size_t)KCH * HRP * 128, w_bytes = (size_t)p->ntaps * KCH * BN * 128;
+  const size_t a_bytes = (size_t)KCH * HRP * BKC * 2, w_bytes = (size_t)p->ntaps * KCH * BN * BKC * 2;
   int stages = 4;
   while (stages > 2 && stages * a_bytes + w_bytes > 200 * 1024) --stages;
   a.stages = stages;
-  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16;
+  const size_t epi = a.epi_tma ? epi_bytes(BN) + 1024 : 0;
+  while (stages > 2 && stages * a_bytes + w_bytes + epi > 208 * 1024) --stages;
+  // two CTAs per SM (more tiles in flight) when the resident weights leave room for it
+  if (2 * a_bytes + w_bytes + epi + 4096 <= 110 * 1024) { stages = (int)((110 * 1024 - w_bytes - epi - 4096) / a_bytes); if (stages > 4) stages = 4; }
+  a.stages = stages;
+  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 + epi;
   const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmW;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p->Cin, 1, (cuuint64_t)p->T, (cuuint64_t)p->B};
     cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->T};
-    cuuint32_t box[4] = {64, 1, (cuuint32_t)HRP, 1};
+    cuuint32_t box[4] = {BKC, 1, (cuuint32_t)HRP, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, dt, 4, const_cast<void*>(p->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw A) failed: %d", (int)r);
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)p->CinP, (cuuint64_t)p->ntaps * p->CoutP};
     cuuint64_t strides[1] = {(cuuint64_t)p->CinP * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t box[2] = {BKC, (cuuint32_t)BN};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tmW, dt, 2, const_cast<void*>(p->w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw W) failed: %d", (int)r);
   }
   static bool attr_set = false;
   if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_halo_sw_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ASB_CUDA(cudaFuncSetAttribute(conv_halo_sw_kernel<BN, BKC, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int total_tiles = p->B * a.n_ttiles;
@@ -913,14 +1097,14 @@ static int launch_halo_sw(const as_conv_params* p, ConvArgs& a, EncodeTiledFn en
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_halo_sw_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, a);
+  conv_halo_sw_kernel<BN, BKC, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
 
-static bool halo_sw_eligible(const as_conv_params* p, int bn) {
+static bool halo_sw_eligible(const as_conv_params* p, int bn, size_t extra_smem) {
   if (p->F != 1 || p->Fo != 1 || p->To != p->T) return false;
-  if (p->Cin % 64 != 0 || p->Cin > 128 || p->CinP != p->Cin || bn > 128 || p->CoutP != bn) return false;
+  if (!(p->Cin == 32 || p->Cin == 64 || p->Cin == 128) || p->CinP != p->Cin || bn > 128 || p->CoutP != bn) return false;
   int lo = 0, hi = 0;
   for (int j = 0; j < p->ntaps; ++j) {
     if (p->tap_df[j] != 0) return false;
@@ -928,8 +1112,8 @@ static bool halo_sw_eligible(const as_conv_params* p, int bn) {
   }
   if (128 + hi - lo > 248) return false;
   const size_t HRP = (128 + hi - lo + 7) / 8 * 8;
-  const size_t a_bytes = (size_t)(p->Cin / 64) * HRP * 128, w_bytes = (size_t)p->ntaps * (p->Cin / 64) * bn * 128;
-  return 2 * a_bytes + w_bytes + 16 * 1024 <= 200 * 1024;
+  const size_t a_bytes = (size_t)HRP * p->Cin * 2, w_bytes = (size_t)p->ntaps * p->Cin * bn * 2;
+  return 2 * a_bytes + w_bytes + extra_smem + 16 * 1024 <= 216 * 1024;
 }
 
 static bool halo_eligible(const as_conv_params* p, int bn) {
@@ -1041,6 +1225,28 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
 
   const CUtensorMapDataType dt =
       p->x_dtype == AS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  // TMA epilogue: 1-D, every present tensor in the launch's 16-bit format, no second residual
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  static const bool no_epi_tma = getenv("ASB_NO_EPI_TMA") != nullptr;
+  a.epi_tma = (!no_epi_tma && a.fast && p->F == 1 && p->Fo == 1 && a.k_res2 == 0 && a.k_res1 != 2 && a.k_raw != 2 &&
+               a.k_act != 2 && (a.k_raw == 1 || a.k_act == 1)) ? 1 : 0;
+  if (a.epi_tma) {
+    auto mk = [&](CUtensorMap* m, const void* ptr, long long ld) -> bool {
+      cuuint64_t dims[3] = {(cuuint64_t)p->Cout, (cuuint64_t)p->To, (cuuint64_t)p->B};
+      cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * p->To};
+      cuuint32_t box[3] = {epi_cols(bn), 32, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      return enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 epi_cols(bn) == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = true;
+    if (a.k_res1 == 1) ok = ok && mk(&em.r1, p->res1, p->res1_ld);
+    if (a.k_raw == 1) ok = ok && mk(&em.raw, p->y_raw, p->y_raw_ld);
+    if (a.k_act == 1) ok = ok && mk(&em.act, p->y_act, p->y_act_ld);
+    if (!ok) a.epi_tma = 0;
+  }
   const CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmA, tmW;
   {
@@ -1068,23 +1274,27 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool no_halo = getenv("ASB_NO_HALO") != nullptr;
   static const bool no_halo_sw = getenv("ASB_NO_HALO_SW") != nullptr;
-  if (!no_halo && !no_halo_sw && halo_sw_eligible(p, bn)) {
+  if (!no_halo && !no_halo_sw && halo_sw_eligible(p, bn, a.epi_tma ? epi_bytes(bn) + 1024 : 0)) {
     const bool bf = p->x_dtype == AS_BF16;
-#define HALOSW_CASE(BN_) if (bn == BN_) return bf ? launch_halo_sw<BN_, true>(p, a, enc, st) : launch_halo_sw<BN_, false>(p, a, enc, st);
+#define HALOSW_CASE(BN_)                                                                          \
+  if (bn == BN_) {                                                                                \
+    if (p->Cin == 32) return bf ? launch_halo_sw<BN_, 32, true>(p, a, em, enc, st) : launch_halo_sw<BN_, 32, false>(p, a, em, enc, st); \
+    return bf ? launch_halo_sw<BN_, 64, true>(p, a, em, enc, st) : launch_halo_sw<BN_, 64, false>(p, a, em, enc, st);                    \
+  }
     HALOSW_CASE(16) HALOSW_CASE(32) HALOSW_CASE(64) HALOSW_CASE(128)
 #undef HALOSW_CASE
   }
   if (!no_halo && halo_eligible(p, bn)) {
     const bool bf = p->x_dtype == AS_BF16;
-#define HALO_CASE(BN_) if (bn == BN_) return bf ? launch_halo<BN_, true>(p, a, enc, st) : launch_halo<BN_, false>(p, a, enc, st);
+#define HALO_CASE(BN_) if (bn == BN_) return bf ? launch_halo<BN_, true>(p, a, em, enc, st) : launch_halo<BN_, false>(p, a, em, enc, st);
     HALO_CASE(16) HALO_CASE(32) HALO_CASE(64)
 #undef HALO_CASE
   }
   const int total_tiles = p->B * a.n_ttiles * a.n_ftiles * (p->CoutP / bn);
 #define CV_CASE(BN_, BK_)                                                                    \
   if (bn == BN_ && bk == BK_)                                                                \
-    return p->x_dtype == AS_BF16 ? launch_conv<BN_, BK_, true>(tmA, tmW, a, total_tiles, st) \
-                                 : launch_conv<BN_, BK_, false>(tmA, tmW, a, total_tiles, st);
+    return p->x_dtype == AS_BF16 ? launch_conv<BN_, BK_, true>(tmA, tmW, em, a, total_tiles, st) \
+                                 : launch_conv<BN_, BK_, false>(tmA, tmW, em, a, total_tiles, st);
   CV_CASE(16, 32) CV_CASE(32, 32) CV_CASE(64, 32) CV_CASE(128, 32) CV_CASE(256, 32)
   CV_CASE(16, 64) CV_CASE(32, 64) CV_CASE(64, 64) CV_CASE(128, 64) CV_CASE(256, 64)
 #undef CV_CASE

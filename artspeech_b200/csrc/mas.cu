@@ -95,7 +95,8 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
       float* dst = dst0 + (size_t)w * cw * PX;
       const int n = nrow * cw;
       for (int i = tid; i < n; i += nthr) {
-        const int col = i % cw, row = i / cw;
+        int col, row;
+        if (cw == 32) { col = i & 31; row = i >> 5; } else { col = i % cw; row = i / cw; }
         const int y = blk * cw + col;
         if (y < yl) cp_async4(smem_u32(dst + col * PX + row), vb + (size_t)(r0 + row) * Ty + y);
       }
@@ -127,6 +128,35 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
       if (warp > 0 && lane < cw) bv = bnd[((warp - 1) * 2 + (blk & 1)) * 32 + lane];
       float* my_bnd = bnd + (warp * 2 + (blk & 1)) * 32;
       const int ncol = min(cw, yl - blk * cw);
+      if (cw == 32 && ncol == 32 && blk > 0) {
+        // fast path (ncu: the generic loop below spends ~60 dependent instructions per column with one
+        // or two warps per scheduler): a full 32-column block, fully unrolled -> static shuffle lanes,
+        // static bit positions, immediate shared-memory offsets; exactly one direction word per row.
+        const float up0 = (warp == 0) ? MAS_NEG : carry;
+#pragma unroll
+        for (int col = 0; col < 32; ++col) {
+          const float* vc = src + col * PX;
+          float up = __shfl_up_sync(0xffffffffu, q[R - 1], 1);
+          const float prevw = __shfl_sync(0xffffffffu, bv, (col + 31) & 31);
+          if (lane == 0) up = (col == 0) ? up0 : ((warp == 0) ? MAS_NEG : prevw);
+#pragma unroll
+          for (int r = R - 1; r >= 0; --r) {
+            const float same = q[r];
+            const float diag = (r == 0) ? up : q[r - 1];
+            const bool take_same = same > diag;
+            const float best = take_same ? same : diag;
+            const bool mv = tie_move ? !take_same : (diag > same);
+            bits[r] |= (mv ? 1u : 0u) << col;
+            q[r] = vc[r] + best;
+          }
+          if (lane == 31) my_bnd[col] = q[R - 1];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          dirs[(size_t)(row0 + r) * W + blk] = (row0 + r == 0) ? 0u : bits[r];
+          bits[r] = 0u;
+        }
+      } else
       for (int col = 0; col < ncol; ++col) {
         const float* vc = src + col * PX;
         const int y = blk * cw + col;

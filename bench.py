@@ -83,6 +83,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def vocoder_traffic():
+    """DRAM bytes (read + write) of the vocoder's conv launches per step, from the committed ncu capture
+    (profiles/r01_vocoder_traffic.json); None when no capture is available."""
+    path = os.path.join(ROOT, "profiles", "r01_vocoder_traffic.json")
+    if os.path.isfile(path):
+        try:
+            return json.load(open(path)).get("dram_bytes_per_step")
+        except Exception:
+            return None
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -225,23 +237,59 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
 
-    # dominant kernel: the vocoder's implicit-GEMM convolutions.  Time the vocoder alone (78 launches of
-    # conv_igemm_kernel, nothing else) with CUDA events on the launch stream.
+    # dominant kernel family: the vocoder's implicit-GEMM convolutions (78 conv launches, nothing else).
+    # Timed alone, replayed from a CUDA graph (no launch gaps), with CUDA events on the launch stream.
     _, lens_m, mel_out = step_resident()
     mel_static = mel_out.clone()
     lens_static = lens_m.clone()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            syn.generator(mel_static, lens_static)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    vg = torch.cuda.CUDAGraph()
+    l_before = ops.launch_count
+    with torch.cuda.graph(vg):
+        syn.generator(mel_static, lens_static)
+    voc_launches = ops.launch_count - l_before
     for _ in range(3):
-        gen_out = syn.generator(mel_static, lens_static)
+        vg.replay()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(5, args.steps)
     e0.record()
-    reps = max(3, args.steps)
     for _ in range(reps):
-        syn.generator(mel_static, lens_static)
+        vg.replay()
     e1.record()
     torch.cuda.synchronize(dev)
     voc_ms = e0.elapsed_time(e1) / reps
     voc_flops = VOCODER_FLOP_PER_FRAME * B_PER_GPU * FRAMES
+
+    # MAS (BASELINE config 5): 64 x 200 tokens x 1000 frames, fp32, bit-exact path
+    mas_info = None
+    if rank == 0:
+        from artspeech_b200 import mas
+        gm = torch.Generator().manual_seed(7)
+        val = torch.randn(64, 200, 1000, generator=gm).to(dev)
+        xl = torch.randint(100, 201, (64,), generator=gm)
+        yl = torch.maximum(torch.randint(500, 1001, (64,), generator=gm), xl)
+        xl[0], yl[0] = 200, 1000
+        xl_d, yl_d = xl.to(dev, torch.int32), yl.to(dev, torch.int32)
+        for _ in range(3):
+            mas.maximum_path_lens(val, xl_d, yl_d)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(20):
+            mas.maximum_path_lens(val, xl_d, yl_d)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        mas_ms = e0.elapsed_time(e1) / 20
+        mas_bytes = 2.0 * 64 * 200 * 1000 * 4
+        mas_info = {"shape": "64x200x1000 fp32", "ms": mas_ms, "algorithmic_GBps": mas_bytes / mas_ms / 1e6,
+                    "frac_of_hbm_peak": mas_bytes / mas_ms / 1e6 / peaks()["hbm_gbs"],
+                    "note": "serial dependency chain over Ty: latency-bound by construction, not roofline-graded"}
 
     if rank != 0:
         if world > 1:
@@ -268,11 +316,13 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(wav_h.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (vocoder, 78 launches per step)",
+        "roofline": {"bound": "tensor", "kernel": f"conv_igemm / conv_halo_sw kernels (vocoder, {voc_launches} launches per step)",
                      "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
-                     "peak_source": pk["source"] + " sustained bf16",
-                     "vocoder_ms": voc_ms, "vocoder_share_of_step": voc_ms / (ms / args.steps)},
+                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": vocoder_traffic(),
+                     "peak_source": pk["source"] + " sustained bf16 (kernel family timed inside a long step)",
+                     "flops_per_step": voc_flops, "vocoder_ms": voc_ms,
+                     "vocoder_share_of_step": voc_ms / (ms / args.steps)},
+        "mas": mas_info,
     }
     if world == 1 and not args.no_cpu_baseline:
         a, t = cpu_reference_sample(args.cpu_utts, os.cpu_count() or 1)

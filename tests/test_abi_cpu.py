@@ -28,7 +28,10 @@ def test_library_exports_every_declared_symbol():
     assert lib.as_conv_tile_n(640) == ops.conv_tile_n(640) == 128
     for c in (1, 16, 17, 32, 80, 128, 192, 256, 512, 640, 1024, 1536, 2560):
         assert lib.as_conv_tile_n(c) == ops.conv_tile_n(c)
-    assert lib.as_mas_workspace_bytes(64, 200, 1000) > 0
+    # direction bits of 64x200x1000 fit in shared memory (no workspace); long items spill to the caller's workspace
+    assert lib.as_mas_workspace_bytes(64, 200, 1000) == 0
+    assert lib.as_mas_workspace_bytes(2, 1280, 4000) >= 2 * 1280 * 4000 // 8
+    assert lib.as_mas_workspace_bytes(0, 200, 1000) == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

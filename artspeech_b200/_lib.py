@@ -39,6 +39,20 @@ class ConvParams(C.Structure):
     ]
 
 
+class ResblockPairParams(C.Structure):
+    """Mirror of ``struct as_resblock_pair_params``."""
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ld", C.c_int64), ("dtype", C.c_int32),
+        ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("dil", C.c_int32),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("slope", C.c_float),
+        ("res2", C.c_void_p), ("res2_ld", C.c_int64), ("res3", C.c_void_p), ("res3_ld", C.c_int64),
+        ("out_scale", C.c_float), ("out_act", C.c_int32), ("out_slope", C.c_float),
+        ("y", C.c_void_p), ("y_ld", C.c_int64),
+        ("lens", C.c_void_p),
+    ]
+
+
 class AsError(RuntimeError):
     pass
 
@@ -55,6 +69,7 @@ SIGNATURES = {
                                       C.c_void_p]),
     "as_conv_tile_n": (C.c_int32, [C.c_int32]),
     "as_conv_igemm": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
+    "as_hifigan_resblock_pair": (C.c_int, [C.POINTER(ResblockPairParams), C.c_void_p]),
 }
 
 

@@ -55,20 +55,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     os.makedirs(os.path.join(CSRC, "obj"), exist_ok=True)
+    hdr = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "artspeech_b200.h")]:
+        if f.endswith((".cuh", ".h")):
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                hdr.update(fh.read())
+    hdr.update(" ".join(NVCC_FLAGS).encode())
+    stamps = []
     for src in _sources():
         obj = os.path.join(CSRC, "obj", os.path.basename(src)[:-3] + ".o")
+        # per-object stamp: a translation unit is recompiled only when it or a header changed
+        with open(src, "rb") as fh:
+            digest = hashlib.sha256(hdr.digest() + fh.read()).hexdigest()
+        objs.append(obj)
+        if not force and os.path.isfile(obj) and os.path.isfile(obj + ".stamp") and \
+                open(obj + ".stamp").read().strip() == digest:
+            continue
+        stamps.append((obj + ".stamp", digest))
         cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose and out:
             print(out.decode(), file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out.decode()}")
+    for path, digest in stamps:
+        with open(path, "w") as f:
+            f.write(digest)
     link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static",
             "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)

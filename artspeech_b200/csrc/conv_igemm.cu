@@ -17,1090 +17,53 @@
 // allocator + MMA issuer (one lane, alternates between two TMEM accumulator stages), warps 2..9 =
 // two epilogue warpgroups that drain the accumulator stages alternately (TMEM lane quadrant =
 // warp_idx % 4), so the epilogue of tile i overlaps the MMAs of tile i+1.
-#include <cuda.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "common.cuh"
+#include "conv_igemm_impl.cuh"
 
 namespace asb {
 
-constexpr int CV_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups
-constexpr int CV_MAX_TAPS = 32;
-
-struct ConvArgs {
-  int B, To, Fo, Cout, CoutP;
-  int tT, tF, n_ttiles, n_ftiles;
-  int ntaps, kchunks, stages;
-  int tap_dt[CV_MAX_TAPS];
-  int tap_df[CV_MAX_TAPS];
-  uint32_t idesc;
-  const float* bias;
-  const void* res1; int res1_dtype; long long res1_ld;
-  const void* res2; int res2_dtype; long long res2_ld;
-  float out_scale;
-  void* y_raw; int y_raw_dtype; long long y_raw_ld; int y_raw_vec;
-  void* y_act; int y_act_dtype; long long y_act_ld; int y_act_vec;
-  int act; float slope;
-  const int* lens;
-  float* stats;
-  // fast-epilogue plan (host-computed): tensor kinds 0 absent / 1 launch 16-bit format / 2 fp32
-  int fast, k_res1, k_res2, k_raw, k_act, act_simple;
-  float act_slope_eff;
-  int halo_rows, pad_lo;   // halo variants: rows of the halo tile, -min(tap_dt)
-  int epi_tma;             // 1: all-16-bit 1-D epilogue through shared memory + TMA
-  int halo_baseoff;        // swizzled halo: put (row & 7) into the descriptor's base-offset field
-};
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1),
-      "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db,
-                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-struct EpiMaps { CUtensorMap r1, raw, act; };
-// per epilogue warp: 2 staging tiles of [32 rows][EPC channels]; EPC = 64 (128 B rows, 128B swizzle) or,
-// for tiles narrower than 64 channels, 32 (64 B rows, 64B swizzle)
-__host__ __device__ constexpr uint32_t epi_cols(int bn) { return bn >= 64 ? 64u : 32u; }
-__host__ __device__ constexpr uint32_t epi_warp_bytes(int bn) { return 2u * 32u * epi_cols(bn) * 2u; }
-__host__ __device__ constexpr uint32_t epi_bytes(int bn) { return 8u * epi_warp_bytes(bn) + 64u; }
-
-// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, =1) | [32,46) SBO>>4
-//   [46,48) version=1 | [61,64) layout (2 = 128B swizzle, 4 = 64B swizzle)
-template <int BK>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  constexpr uint64_t sbo = (BK == 64 ? 1024 : 512) >> 4;  // 8 rows x row bytes
-  constexpr uint64_t layout = (BK == 64) ? 2 : 4;
-  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (sbo << 32) | (uint64_t(1) << 46) |
-         (layout << 61);
-}
-
-// ---------------------------------------------------------------------------------------------
-// epilogue store helpers: 16 consecutive channels of one row
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store16(void* base, int dtype, long long off, const float (&v)[16],
-                                        int nvalid, bool vec) {
-  if (dtype == AS_F32) {
-    float* p = reinterpret_cast<float*>(base) + off;
-    if (vec && nvalid == 16) {
-      float4* p4 = reinterpret_cast<float4*>(p);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) p4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < nvalid) p[i] = v[i];
-    }
-  } else {
-    uint16_t* p = reinterpret_cast<uint16_t*>(base) + off;
-    if (vec && nvalid == 16) {
-      uint4* p4 = reinterpret_cast<uint4*>(p);
-      p4[0] = make_uint4(pack16(v[0], v[1], dtype), pack16(v[2], v[3], dtype),
-                         pack16(v[4], v[5], dtype), pack16(v[6], v[7], dtype));
-      p4[1] = make_uint4(pack16(v[8], v[9], dtype), pack16(v[10], v[11], dtype),
-                         pack16(v[12], v[13], dtype), pack16(v[14], v[15], dtype));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < nvalid) p[i] = to16(v[i], dtype);
-    }
-  }
-}
-
-__device__ __forceinline__ void add_res16(const void* base, int dtype, long long off, float (&v)[16],
-                                          int nvalid, bool vec) {
-  if (dtype == AS_F32) {
-    const float* p = reinterpret_cast<const float*>(base) + off;
-    if (vec && nvalid == 16) {
-      const float4* p4 = reinterpret_cast<const float4*>(p);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 t = __ldg(p4 + i);
-        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += p[i];
-    }
-  } else {
-    const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + off;
-    if (vec && nvalid == 16) {
-      const uint4* p4 = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint4 t = __ldg(p4 + h);
-        uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[8 * h + 2 * i] += from16(uint16_t(w[i] & 0xFFFF), dtype);
-          v[8 * h + 2 * i + 1] += from16(uint16_t(w[i] >> 16), dtype);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += from16(p[i], dtype);
-    }
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Fast epilogue chunk (16 channels of one row).  The generic helpers above dispatch on dtypes per
-// element and cost ~500 SASS instructions per chunk (ncu: the epilogue, not the MMAs, bounded the
-// kernel).  This path is specialised at compile time on the 16-bit format and hoists every
-// decision out of the chunk loop: ~120 instructions per chunk.
-//   kind: 0 = absent, 1 = 16-bit (the launch's operand format), 2 = fp32
-// ---------------------------------------------------------------------------------------------
-template <bool BF16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (BF16) { __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
-  __half2 t = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-template <bool BF16>
-__device__ __forceinline__ void unpack_add(uint32_t u, float& a, float& b) {
-  if (BF16) { a += __uint_as_float(u << 16); b += __uint_as_float(u & 0xFFFF0000u); return; }
-  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
-  a += f.x; b += f.y;
-}
-template <bool BF16>
-__device__ __forceinline__ void add_res_fast(const char* p, int kind, float (&v)[16]) {
-  if (kind == 1) {
-    const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(p)), t1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-    unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
-    unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
-    unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
-    unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
-      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
-  }
-}
-template <bool BF16>
-__device__ __forceinline__ void store_fast(char* p, int kind, const float (&v)[16]) {
-  if (kind == 1) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
-    q[1] = make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15]));
-  } else {
-    float4* q = reinterpret_cast<float4*>(p);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// epilogue (shared by both kernels): two warpgroups alternate tiles; TMEM -> registers -> global
-// ---------------------------------------------------------------------------------------------
-template <int BN, bool BF16>
-__device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint32_t tfull0,
-                                             uint32_t tempty0, int warp, int lane, int m_tiles,
-                                             int total_tiles, const float* bias_s) {
-  // 16-bit residual rows are fetched into registers BEFORE the accumulator wait (ncu: the epilogue
-  // warps were stalled on these loads, long_scoreboard ~12 cycles/issue): up to 128 channels/row.
-  // BN = 256 runs one CTA per SM (<= 204 regs/thread): 128 channels; narrower tiles run two CTAs
-  // per SM (<= 102 regs/thread): 64 channels.
-  constexpr int NPRE = (BN >= 256 ? 128 : (BN < 64 ? BN : 64)) / 8;   // uint4 registers of residual prefetch
-  auto tfull_bar = [&](int i) { return tfull0 + 8u * i; };
-  auto tempty_bar = [&](int i) { return tempty0 + 8u * i; };
-    const int wg = (warp - 2) >> 2;  // 0 / 1 = accumulator stage this warpgroup drains
-  const int q = warp & 3;          // TMEM lane quadrant this warp may access
-  const int m = q * 32 + lane;     // tile row
-  const int it_ = m / a.tF, if_ = m - it_ * a.tF;
-  int lt = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-    if ((lt & 1) != wg) continue;
-    int mt = tile % m_tiles;
-    const int n0 = (tile / m_tiles) * BN;
-    const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
-    const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
-    const int b = mt;
-    const int t = tt * a.tT + it_, f = ft * a.tF + if_;
-    const bool row_ok = (t < a.To) && (f < a.Fo);
-    bool masked = false;
-    if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
-    const long long row = ((long long)b * a.To + t) * a.Fo + f;
-
-    // per-tile constants of the fast path (byte pointers of this thread's row, kinds, slope)
-    const int ncols = min(BN, a.Cout - n0);  // valid columns in this N tile (may be <= 0)
-    const bool fast = a.fast != 0;
-    const int k_r1 = a.k_res1, k_r2 = a.k_res2, k_raw = a.k_raw, k_act = a.k_act;
-    const char* p_r1 = k_r1 ? reinterpret_cast<const char*>(a.res1) + (row * a.res1_ld + n0) * (k_r1 == 1 ? 2 : 4) : nullptr;
-    const char* p_r2 = k_r2 ? reinterpret_cast<const char*>(a.res2) + (row * a.res2_ld + n0) * (k_r2 == 1 ? 2 : 4) : nullptr;
-    char* p_raw = k_raw ? reinterpret_cast<char*>(a.y_raw) + (row * a.y_raw_ld + n0) * (k_raw == 1 ? 2 : 4) : nullptr;
-    char* p_act = k_act ? reinterpret_cast<char*>(a.y_act) + (row * a.y_act_ld + n0) * (k_act == 1 ? 2 : 4) : nullptr;
-    const float scale = masked ? 0.f : a.out_scale;   // masked rows become exact zeros (res are finite)
-    const float aslope = a.act_slope_eff;
-    const float* bias_t = bias_s + n0;
-    const bool pre_ok = fast && k_r1 == 1 && row_ok && !masked;
-    uint4 pre[NPRE];
-    if (pre_ok) {
-#pragma unroll
-      for (int i = 0; i < NPRE; ++i)
-        if (i * 8 + 8 <= ncols) pre[i] = __ldg(reinterpret_cast<const uint4*>(p_r1) + i);
-    }
-
-    mbar_wait(tfull_bar(wg), ((uint32_t)lt >> 1) & 1u);
-    tc_fence_after();
-    const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
-#pragma unroll
-    for (int cc = 0; cc < BN / 16; ++cc) {
-      const int c0 = cc * 16;
-      if (c0 >= ncols) break;  // warp-uniform
-      uint32_t r[16];
-      tc_ld16(tacc + uint32_t(c0), r);
-      tc_wait_ld();
-      if (!row_ok) continue;
-      const int co = n0 + c0;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      if (fast && c0 + 16 <= ncols) {
-        {   // bias staged in shared memory once per CTA (zeros when the layer has none)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + 4 * i);
-            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-          }
-        }
-        if (pre_ok && 2 * cc + 1 < NPRE) {
-          const uint4 t0 = pre[(2 * cc) < NPRE ? 2 * cc : 0], t1 = pre[(2 * cc + 1) < NPRE ? 2 * cc + 1 : 0];
-          unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
-          unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
-          unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
-          unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
-        } else if (k_r1 && !masked) add_res_fast<BF16>(p_r1 + c0 * (k_r1 == 1 ? 2 : 4), k_r1, v);
-        if (k_r2 && !masked) add_res_fast<BF16>(p_r2 + c0 * (k_r2 == 1 ? 2 : 4), k_r2, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= scale;
-        if (k_raw) store_fast<BF16>(p_raw + c0 * (k_raw == 1 ? 2 : 4), k_raw, v);
-        if (k_act) {
-          if (a.act_simple) {
-            // none / lrelu / relu / abs: act(v) = max(v, v * s) with s = 1 / slope / 0 / -1
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * aslope);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-          }
-          store_fast<BF16>(p_act + c0 * (k_act == 1 ? 2 : 4), k_act, v);
-        }
-      } else {
-        // generic path: partial chunks (Cout not a multiple of 16), unaligned or mixed-format tensors
-        const int nvalid = min(16, a.Cout - co);
-        if (a.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (i < nvalid) v[i] += __ldg(a.bias + co + i);
-        }
-        if (a.res1 != nullptr) add_res16(a.res1, a.res1_dtype, row * a.res1_ld + co, v, nvalid, false);
-        if (a.res2 != nullptr) add_res16(a.res2, a.res2_dtype, row * a.res2_ld + co, v, nvalid, false);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * a.out_scale;
-        if (a.y_raw != nullptr) store16(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + co, v, nvalid, false);
-        if (a.y_act != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-          store16(a.y_act, a.y_act_dtype, row * a.y_act_ld + co, v, nvalid, false);
-        }
-      }
-    }
-    // all TMEM reads of this stage are complete (tcgen05.wait::ld above): hand it back to the MMA warp
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// TMA epilogue for the all-16-bit 1-D case (every vocoder conv).  ncu on the register->global
-// epilogue above: l1tex__data_pipe_lsu_wavefronts at 68 % of peak — a thread owns a row, so every
-// 16-byte access of a warp lands in a different 128-byte line (32 wavefronts per instruction).
-// Here each epilogue warp stages its 32 rows x 64 channels in a 128B-swizzled shared tile and moves
-// it with ONE bulk tensor copy per tensor: the residual arrives by TMA load (issued before the
-// accumulator wait), raw / activated outputs leave by TMA store.  Out-of-range rows / channels are
-// clipped by the TMA unit, so partial tiles need no special path.
-// ---------------------------------------------------------------------------------------------
-template <int BN, bool BF16>
-__device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMaps& maps, uint32_t tmem_base,
-                                                 uint32_t tfull0, uint32_t tempty0, int warp, int lane, int m_tiles,
-                                                 int total_tiles, const float* bias_s, uint32_t epi_base) {
-  const int ew = warp - 2;                 // 0..7
-  const int wg = ew >> 2;
-  const int q = warp & 3;
-  constexpr uint32_t EPC = epi_cols(BN);                  // channels per staged group
-  constexpr uint32_t ROWB = EPC * 2u;                     // bytes per staged row (128 or 64)
-  constexpr uint32_t TILEB = 32u * ROWB;
-  constexpr int CPG = EPC / 16;                           // 16-channel chunks per group
-  const uint32_t bufA = epi_base + (uint32_t)ew * epi_warp_bytes(BN);   // residual in / raw out (in place)
-  const uint32_t bufB = bufA + TILEB;                                    // activated out
-  const uint32_t rbar = epi_base + 8u * epi_warp_bytes(BN) + 8u * ew;
-  const bool has_r1 = a.k_res1 == 1, has_raw = a.k_raw == 1, has_act = a.k_act == 1;
-  const uint32_t rowoff = (uint32_t)lane * ROWB;
-  // 16-byte unit swizzle of the TMA layout: 128B mode XORs with (row & 7), 64B mode with (row >> 1) & 3
-  const uint32_t sw = (EPC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
-  uint32_t rphase = 0;
-  int lt = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-    if ((lt & 1) != wg) continue;
-    const int mt = tile % m_tiles;
-    const int n0 = (tile / m_tiles) * BN;
-    const int tt = mt % a.n_ttiles, b = mt / a.n_ttiles;
-    const int t_base = tt * 128 + q * 32;
-    const int t = t_base + lane;
-    const bool masked = (a.lens != nullptr) && (t < a.To) && (t >= __ldg(a.lens + b));
-    const int ncols = min(BN, a.Cout - n0);
-    const int ngroups = (ncols + (int)EPC - 1) / (int)EPC;
-    const float scale = a.out_scale, aslope = a.act_slope_eff;
-
-    if (has_r1 && lane == 0 && ngroups > 0) {
-      bulk_wait_read0();                                   // previous stores have drained this buffer
-      mbar_expect_tx(rbar, TILEB);
-      tma_load_3d(bufA, &maps.r1, rbar, n0, t_base, b);
-    }
-    mbar_wait(tfull0 + 8u * wg, ((uint32_t)lt >> 1) & 1u);
-    tc_fence_after();
-    const uint32_t tacc = tmem_base + (uint32_t)(wg * BN) + (uint32_t(q * 32) << 16);
-    for (int g = 0; g < ngroups; ++g) {
-      if (has_r1) {
-        mbar_wait(rbar, rphase);
-        rphase ^= 1u;
-      } else {
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
-      }
-#pragma unroll
-      for (int cc = 0; cc < CPG; ++cc) {
-        const int c0 = g * (int)EPC + cc * 16;
-        if (c0 < ncols) {   // warp-uniform
-          uint32_t r[16];
-          tc_ld16(tacc + uint32_t(c0), r);
-          tc_wait_ld();
-          float v[16];
-          const float* bt = bias_s + n0 + c0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = *reinterpret_cast<const float4*>(bt + 4 * i);
-            v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
-          }
-          const uint32_t o0 = rowoff + (((uint32_t)(2 * cc) ^ sw) << 4), o1 = rowoff + (((uint32_t)(2 * cc + 1) ^ sw) << 4);
-          if (has_r1) {
-            const uint4 t0 = lds128(bufA + o0), t1 = lds128(bufA + o1);
-            unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
-            unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
-            unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
-            unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * scale;
-          if (has_raw) {
-            sts128(bufA + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
-            sts128(bufA + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
-          }
-          if (has_act) {
-            if (a.act_simple) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * aslope);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
-            }
-            sts128(bufB + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
-            sts128(bufB + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
-          }
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (has_raw) tma_store_3d(&maps.raw, bufA, n0 + g * (int)EPC, t_base, b);
-        if (has_act) tma_store_3d(&maps.act, bufB, n0 + g * (int)EPC, t_base, b);
-        bulk_commit();
-        if (has_r1 && g + 1 < ngroups) {
-          bulk_wait_read0();
-          mbar_expect_tx(rbar, TILEB);
-          tma_load_3d(bufA, &maps.r1, rbar, n0 + (g + 1) * (int)EPC, t_base, b);
-        }
-      }
-      __syncwarp();
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * wg) : "memory");
-  }
-  if (lane == 0) bulk_wait_all0();   // all stores complete before the CTA exits
-}
-
-// ---------------------------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------------------------
-template <int BN, int BK, bool BF16>
-__global__ void __launch_bounds__(CV_THREADS, (BN >= 256 ? 1 : 2))
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ EpiMaps emaps,
-                  const __grid_constant__ ConvArgs a) {
-  constexpr int A_BYTES = 128 * BK * 2;
-  constexpr int W_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);   // two accumulator stages (power of two)
-
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const int S = a.stages;
-  const uint32_t bar_base = smem_base + S * STAGE_BYTES;  // full[S], empty[S], tfull[2], tempty[2], slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
-  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
-  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
-  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m_tiles = a.B * a.n_ttiles * a.n_ftiles;
-  const int total_tiles = m_tiles * (a.CoutP / BN);
-  const int k_iters = a.ntaps * a.kchunks;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
-    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  // Persistent CTA: every role walks the same static tile schedule (tile = blockIdx.x + i*gridDim.x,
-  // M fastest so concurrently running CTAs share the weight tile in L2).  The smem ring and the two
-  // TMEM accumulator stages decouple the roles: TMA runs ahead across tile boundaries, the MMA of
-  // tile i+1 overlaps the epilogue of tile i.
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int mt = tile % m_tiles;
-        const int n0 = (tile / m_tiles) * BN;
-        const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
-        const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
-        const int b = mt, t0 = tt * a.tT, f0 = ft * a.tF;
-        for (int kit = 0; kit < k_iters; ++kit, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          const int tap = kit / a.kchunks, kc = kit - tap * a.kchunks;
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          tma_load_4d(sa, &tmA, full_bar(s), kc * BK, f0 + a.tap_df[tap], t0 + a.tap_dt[tap], b);
-          tma_load_2d(sa + A_BYTES, &tmW, full_bar(s), kc * BK, tap * a.CoutP + n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue drained this stage
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
-        for (int kit = 0; kit < k_iters; ++kit, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          const uint64_t da = make_smem_desc<BK>(sa);
-          const uint64_t db = make_smem_desc<BK>(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 field
-            tc_mma_f16(tacc, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc, (kit | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
-        }
-        tc_commit(tfull_bar(acc));  // accumulator of this tile complete
-      }
-    }
-  } else {
-    // ===== epilogue =====
-    if (a.epi_tma)
-      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
-    else
-      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "n"(TMEM_COLS)
-                 : "memory");
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Narrow-channel 1-D variant (Cin, Cout <= 64: vocoder stages with 64 / 32 channels, 37 % of its
-// FLOPs but > 50 % of its time with the kernel above, which re-loads the activation tile once per
-// tap).  Here the activation tile is loaded ONCE per output tile with its halo
-// (128 + (k-1)*dil rows) and ALL taps' weights stay resident in shared memory for the CTA's life:
-// L2->smem traffic per tile drops from k*(A+W) to ~1.4*A.
-//
-// Layout: un-swizzled K-major "core matrix" planes.  One TMA box {8 ch, HRP rows, Cin/8 planes}
-// of a tensor map whose dimensions are ordered (8 channels, time, channel-block) lands in shared
-// memory as [plane][row][8 ch]: every 16-byte unit is one row of an 8x8 core matrix, 8 rows are
-// contiguous (128 B), so a tap is simply a start-address offset of `rows * 16` bytes in the UMMA
-// descriptor (LBO = plane stride, SBO = 128 B) — no swizzle phase to keep aligned.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes) {
-  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
-}
-
-template <int BN, bool BF16>
-__global__ void __launch_bounds__(CV_THREADS, 2)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ EpiMaps emaps,
-                 const __grid_constant__ ConvArgs a) {
-  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 127u) & ~127u;
-  const int S = a.stages;
-  const int KC = a.kchunks;                 // 8-channel planes
-  const int HRP = a.halo_rows;              // rows per plane of the A tile (multiple of 8)
-  const uint32_t a_bytes = (uint32_t)KC * HRP * 16;
-  const uint32_t w_tap_bytes = (uint32_t)KC * BN * 16;
-  const uint32_t w_base = smem_base + S * a_bytes;
-  const uint32_t bar_base = (w_base + a.ntaps * w_tap_bytes + 7u) & ~7u;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
-  const uint32_t w_bar = bar_base + 8u * (2 * S + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
-  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
-  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
-  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m_tiles = a.B * a.n_ttiles;
-  const int total_tiles = m_tiles;          // single N tile
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
-    mbar_init(w_bar, 1);
-    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: weights once, then one halo tile per output tile =====
-      mbar_expect_tx(w_bar, a.ntaps * w_tap_bytes);
-      for (int tap = 0; tap < a.ntaps; ++tap)
-        tma_load_4d(w_base + tap * w_tap_bytes, &tmW, w_bar, 0, tap * a.CoutP, 0, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int tt = tile % a.n_ttiles, b = tile / a.n_ttiles;
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), a_bytes);
-        tma_load_4d(smem_base + s * a_bytes, &tmA, full_bar(s), 0, tt * 128 - a.pad_lo, 0, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      mbar_wait(w_bar, 0);
-      int lt = 0;
-      const int ksteps = KC / 2;             // 16 channels per MMA
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        const int s = lt % S;
-        const uint32_t ph = (lt / S) & 1;
-        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
-        const uint32_t sa = smem_base + s * a_bytes;
-        uint32_t first = 0;
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          const uint32_t arow = sa + (uint32_t)(a.pad_lo + a.tap_dt[tap]) * 16u;
-          const uint32_t wtap = w_base + tap * w_tap_bytes;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t da = make_desc_noswz(arow + (uint32_t)(2 * j * HRP) * 16u, (uint32_t)HRP * 16u);
-            const uint64_t db = make_desc_noswz(wtap + (uint32_t)(2 * j * BN) * 16u, (uint32_t)BN * 16u);
-            tc_mma_f16(tacc, da, db, a.idesc, first);
-            first = 1u;
-          }
-        }
-        tc_commit(empty_bar(s));
-        tc_commit(tfull_bar(acc));
-      }
-    }
-  } else {
-    if (a.epi_tma)
-      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
-    else
-      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "n"(TMEM_COLS)
-                 : "memory");
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Swizzled halo variant for 64 / 128 input channels (vocoder stages 1-2).  ncu showed the per-tap
-// kernel is bound by L2->SM bandwidth there (lts ~52 %, 44 B/clk/SM: the LTS cap): each tap re-loads
-// the activation tile and every tile re-streams the weights.  Here the activation tile (with halo)
-// is loaded once per output tile as 64-channel chunks in the standard 128B-swizzled K-major layout
-// (full-width 128 B TMA rows) and all taps' weights are resident in shared memory.  A tap is a
-// start-address offset of r*128 B into the swizzled tile.  Measured on B200: the UMMA swizzle is a
-// function of the absolute shared-memory address bits (like TMA's), so an unaligned start row
-// needs NO base-offset in the descriptor (setting bits 49..51 to r & 7 gives wrong results;
-// tests/test_kernels_gpu.py covers row offsets 1..25).
-// ---------------------------------------------------------------------------------------------
-template <int BN, int BKC, bool BF16>
-__global__ void __launch_bounds__(CV_THREADS, 2)
-conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ EpiMaps emaps,
-                    const __grid_constant__ ConvArgs a) {
-  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const int S = a.stages;
-  constexpr uint32_t RB = BKC * 2u;          // bytes per row of a chunk: 128 (128B swizzle) or 64 (64B swizzle)
-  const int KCH = a.kchunks;                // BKC-channel chunks
-  const int HRP = a.halo_rows;              // rows of the halo tile (multiple of 8)
-  const uint32_t chunk_bytes = (uint32_t)HRP * RB;
-  const uint32_t a_bytes = (uint32_t)KCH * chunk_bytes;
-  const uint32_t w_blk = (uint32_t)BN * RB;                         // one (tap, chunk) weight block
-  const uint32_t w_base = smem_base + S * a_bytes;
-  const uint32_t bar_base = w_base + a.ntaps * KCH * w_blk;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
-  const uint32_t w_bar = bar_base + 8u * (2 * S + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
-  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
-  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
-  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m_tiles = a.B * a.n_ttiles;
-  const int total_tiles = m_tiles;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
-    mbar_init(w_bar, 1);
-    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, a.ntaps * KCH * w_blk);
-      for (int tap = 0; tap < a.ntaps; ++tap)
-        for (int c = 0; c < KCH; ++c)
-          tma_load_2d(w_base + (tap * KCH + c) * w_blk, &tmW, w_bar, c * BKC, tap * a.CoutP);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int tt = tile % a.n_ttiles, b = tile / a.n_ttiles;
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), a_bytes);
-        for (int c = 0; c < KCH; ++c)
-          tma_load_4d(smem_base + s * a_bytes + c * chunk_bytes, &tmA, full_bar(s), c * BKC, 0, tt * 128 - a.pad_lo, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(w_bar, 0);
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        const int s = lt % S;
-        const uint32_t ph = (lt / S) & 1;
-        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
-        const uint32_t sa = smem_base + s * a_bytes;
-        uint32_t first = 0;
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          const uint32_t r = (uint32_t)(a.pad_lo + a.tap_dt[tap]);
-          const uint64_t boff = a.halo_baseoff ? (uint64_t(r & 7u) << 49) : 0ull;
-          for (int c = 0; c < KCH; ++c) {
-            const uint64_t da = make_smem_desc<BKC>(sa + c * chunk_bytes + r * RB) | boff;
-            const uint64_t db = make_smem_desc<BKC>(w_base + (tap * KCH + c) * w_blk);
-#pragma unroll
-            for (int k = 0; k < BKC / 16; ++k) {
-              tc_mma_f16(tacc, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc, first);
-              first = 1u;
-            }
-          }
-        }
-        tc_commit(empty_bar(s));
-        tc_commit(tfull_bar(acc));
-      }
-    }
-  } else {
-    if (a.epi_tma)
-      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
-    else
-      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "n"(TMEM_COLS)
-                 : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
-    set_error("cuTensorMapEncodeTiled unavailable (err %d)", (int)e);
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
-static int pick_tile_n(int Cout) {
-  if (Cout <= 16) return 16;
-  if (Cout <= 32) return 32;
-  if (Cout <= 64) return 64;
-  if (Cout <= 128) return 128;
-  if (Cout % 256 == 0) return 256;
-  if (Cout % 128 == 0) return 128;
-  // minimise padding between 128- and 256-wide tiles, prefer the wider one on ties
-  int p256 = (Cout + 255) / 256 * 256, p128 = (Cout + 127) / 128 * 128;
-  return p128 < p256 ? 128 : 256;
-}
-
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
-template <int BN, int BK, bool BF16>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const EpiMaps& em, ConvArgs& a,
-                       int total_tiles, cudaStream_t st) {
-  constexpr int STAGE_BYTES = 128 * BK * 2 + BN * BK * 2;
-  // BN = 256 needs all 512 TMEM columns (two accumulator stages): one CTA per SM with a deep ring.
-  // Narrower tiles run two CTAs per SM (TMEM 2*BN <= 256 columns each, ~100 KB of ring each).
-  // The TMA epilogue needs 64 KB of staging per CTA: one CTA per SM with a deep ring instead of two.
-  const int ctas_per_sm = (BN >= 256 || a.epi_tma) ? 1 : 2;
-  const int budget = a.epi_tma ? (222 * 1024 - (int)epi_bytes(BN) - 2048 - a.CoutP * 4)
-                               : ((BN >= 256 ? 208 : 104) * 1024 - a.CoutP * 4);   // ring + bias within 227 KB / SM
-  int stages = budget / STAGE_BYTES;
-  if (stages > 10) stages = 10;
-  if (stages < 2) stages = 2;
-  a.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
-                      (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, BF16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  int grid = num_sms() * ctas_per_sm;
-  if (grid > total_tiles) grid = total_tiles;
-  conv_igemm_kernel<BN, BK, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
-  ASB_CUDA(cudaGetLastError());
-  return AS_OK;
-}
-
-template <int BN, bool BF16>
-static int launch_halo(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeTiledFn enc, cudaStream_t st) {
-  const int KC = p->Cin / 8;
-  int lo = 0, hi = 0;
-  for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
-  const int HRP = (128 + hi - lo + 7) / 8 * 8;
-  a.kchunks = KC; a.halo_rows = HRP; a.pad_lo = -lo;
-  a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;
-  const size_t a_bytes = (size_t)KC * HRP * 16, w_bytes = (size_t)p->ntaps * KC * BN * 16;
-  int stages = 4;
-  while (stages > 2 && stages * a_bytes + w_bytes > 190 * 1024) --stages;
-  a.stages = stages;
-  const size_t epi = a.epi_tma ? epi_bytes(BN) + 1024 : 0;
-  while (stages > 2 && stages * a_bytes + w_bytes + epi > 208 * 1024) --stages;
-  a.stages = stages;
-  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 256 + 16 + epi;
-  const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap tmA, tmW;
-  {
-    // dims ordered (8 channels, time, channel block, batch): smem gets [plane][row][8ch]
-    cuuint64_t dims[4] = {8, (cuuint64_t)p->T, (cuuint64_t)KC, (cuuint64_t)p->B};
-    cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, 16, (cuuint64_t)p->x_ld * 2 * p->T};
-    cuuint32_t box[4] = {8, (cuuint32_t)HRP, (cuuint32_t)KC, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(p->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo A) failed: %d", (int)r);
-  }
-  {
-    // packed weights [ntaps*CoutP rows][CinP]: (8 ci, rows, ci block, 1) -> [plane][co][8ci] per tap
-    cuuint64_t dims[4] = {8, (cuuint64_t)p->ntaps * p->CoutP, (cuuint64_t)KC, 1};
-    cuuint64_t strides[3] = {(cuuint64_t)p->CinP * 2, 16, (cuuint64_t)p->CinP * 2 * p->ntaps * p->CoutP};
-    cuuint32_t box[4] = {8, (cuuint32_t)BN, (cuuint32_t)KC, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmW, dt, 4, const_cast<void*>(p->w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo W) failed: %d", (int)r);
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  const int total_tiles = p->B * a.n_ttiles;
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  int grid = num_sms() * per_sm;
-  if (grid > total_tiles) grid = total_tiles;
-  conv_halo_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
-  ASB_CUDA(cudaGetLastError());
-  return AS_OK;
-}
-
-template <int BN, int BKC, bool BF16>
-static int launch_halo_sw(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeTiledFn enc, cudaStream_t st) {
-  const int KCH = p->Cin / BKC;
-  int lo = 0, hi = 0;
-  for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
-  const int HRP = (128 + hi - lo + 7) / 8 * 8;
-  a.kchunks = KCH; a.halo_rows = HRP; a.pad_lo = -lo;
-  static const int baseoff_mode = getenv("ASB_HALO_BASEOFF") ? atoi(getenv("ASB_HALO_BASEOFF")) : 0;
-  a.halo_baseoff = baseoff_mode;
-  a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;
-  const size_t a_bytes = (size_t)KCH * HRP * BKC * 2, w_bytes = (size_t)p->ntaps * KCH * BN * BKC * 2;
-  int stages = 4;
-  while (stages > 2 && stages * a_bytes + w_bytes > 200 * 1024) --stages;
-  a.stages = stages;
-  const size_t epi = a.epi_tma ? epi_bytes(BN) + 1024 : 0;
-  while (stages > 2 && stages * a_bytes + w_bytes + epi > 208 * 1024) --stages;
-  // two CTAs per SM (more tiles in flight) when the resident weights leave room for it
-  if (2 * a_bytes + w_bytes + epi + 4096 <= 110 * 1024) { stages = (int)((110 * 1024 - w_bytes - epi - 4096) / a_bytes); if (stages > 4) stages = 4; }
-  a.stages = stages;
-  const size_t smem = stages * a_bytes + w_bytes + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 + epi;
-  const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap tmA, tmW;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)p->Cin, 1, (cuuint64_t)p->T, (cuuint64_t)p->B};
-    cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->T};
-    cuuint32_t box[4] = {BKC, 1, (cuuint32_t)HRP, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(p->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw A) failed: %d", (int)r);
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)p->CinP, (cuuint64_t)p->ntaps * p->CoutP};
-    cuuint64_t strides[1] = {(cuuint64_t)p->CinP * 2};
-    cuuint32_t box[2] = {BKC, (cuuint32_t)BN};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&tmW, dt, 2, const_cast<void*>(p->w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw W) failed: %d", (int)r);
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_halo_sw_kernel<BN, BKC, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  const int total_tiles = p->B * a.n_ttiles;
-  int per_sm = (int)((226 * 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  int grid = num_sms() * per_sm;
-  if (grid > total_tiles) grid = total_tiles;
-  conv_halo_sw_kernel<BN, BKC, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
-  ASB_CUDA(cudaGetLastError());
-  return AS_OK;
-}
+// instantiated in conv_inst_*.cu
+extern template int launch_conv<16, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<16, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<32, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<32, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<64, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<64, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<128, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<128, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<256, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<256, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<16, 64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<16, 64, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<32, 64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<32, 64, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<64, 64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<64, 64, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<128, 64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<128, 64, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<256, 64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_conv<256, 64, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+extern template int launch_halo_sw<16, 32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<16, 32, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<16, 64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<16, 64, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<32, 32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<32, 32, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<32, 64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<32, 64, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<64, 32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<64, 32, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<64, 64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<64, 64, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<128, 32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<128, 32, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<128, 64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo_sw<128, 64, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo<16, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo<16, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo<32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo<32, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo<64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+extern template int launch_halo<64, false>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
 
 static bool halo_sw_eligible(const as_conv_params* p, int bn, size_t extra_smem) {
   if (p->F != 1 || p->Fo != 1 || p->To != p->T) return false;

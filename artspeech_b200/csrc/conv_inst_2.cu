@@ -1,0 +1,12 @@
+// explicit instantiations of the implicit-GEMM convolution launchers (part 3 of 6)
+#include "conv_igemm_impl.cuh"
+
+namespace asb {
+template int launch_conv<256, 64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+template int launch_halo_sw<128, 64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+template int launch_halo_sw<64, 32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+template int launch_conv<32, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+template int launch_halo_sw<32, 32, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+template int launch_conv<16, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
+template int launch_halo_sw<16, 64, true>(const as_conv_params*, ConvArgs&, const EpiMaps&, EncodeTiledFn, cudaStream_t);
+}  // namespace asb

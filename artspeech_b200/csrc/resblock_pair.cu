@@ -1,0 +1,594 @@
+// Fused HiFi-GAN ResBlock1 "pair" for sm_100a (Vocoder/vocoder.py:35-42):
+//
+//     xt = conv1_{k, dilation d}(leaky_relu(x)) ; xt = conv2_{k, 1}(leaky_relu(xt)) ; x = xt + x
+//
+// as ONE kernel per pair, for the vocoder stages with C <= 128 channels.  ncu on the layer-by-layer
+// path (profiles/r01_vocoder_traffic_v11.txt) showed those stages moving 12 tensor-sized HBM
+// transfers per pair (operand + residual in, raw + activated out, twice) and spending most of their
+// time in the epilogue's load/store round trips.  Here the intermediate never leaves the SM:
+//
+//   * the residual stream is carried in its ACTIVATED form a = leaky_relu(x) only (one rounding to
+//     16 bits instead of two).  TMA loads the tile of `a` with its halo straight into the swizzled
+//     K-major layout the UMMA descriptor reads; the raw residual is recovered exactly where it is
+//     needed as x = a < 0 ? a / slope : a;
+//   * stage 1: D1[256 rows, C] = sum over taps of A(shifted by j*d rows) * W1_j^T  (tcgen05.mma, fp32
+//     accumulators in TMEM, a tap is a row offset of the descriptor's start address);
+//   * epilogue 1 (warpgroup 0): TMEM -> +bias -> LeakyReLU -> zero outside the sequence (conv2's
+//     padding) -> 16-bit -> written IN PLACE over the A tile in the same swizzled layout; before
+//     that the same warps seed stage 2's accumulator with residual + bias2 (tcgen05.st);
+//   * stage 2: D2[256 rows, C] += sum over taps of T(shifted by j rows) * W2_j^T;
+//   * epilogue 2 (warpgroup 1): TMEM -> (+ the other MRF branches) * scale -> mask -> activation ->
+//     16-bit -> swizzled staging tile -> TMA store.  256 - (k-1) rows of every tile are valid.
+//
+// HBM traffic per pair: (1 + halo) reads + 1 write of the tensor instead of 12.  Weights stay
+// resident in shared memory when they fit, otherwise they stream from L2 through an mbarrier ring.
+// Warp roles (384 threads, one CTA per SM): 0 = activation-tile TMA producer, 1 = MMA issuer,
+// 2 = weight TMA producer + TMEM allocator, 3 = second MMA issuer, 4-7 = warpgroup 0, 8-11 = warpgroup 1.
+#include "tc_util.cuh"
+
+namespace asb {
+
+constexpr int RP_THREADS = 384;
+
+struct PairArgs {
+  int B, L, tiles_per_item, total_tiles;
+  int k, dil, p1, p2, R_out, HA, HB, tail_rows;
+  int NX, ND, NSTG, SW, stream1, stream2, pipelined;
+  uint32_t idesc;
+  const float* b1;
+  const float* b2;
+  const void* res2; long long res2_ld;
+  const void* res3; long long res3_ld;
+  float slope, inv_slope, out_scale, out_slope_eff;
+  const int* lens;
+};
+struct PairMaps { CUtensorMap x, w1, w2, y, y_tail; };
+
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+template <bool BF16>
+__device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
+  if (BF16) { a = __uint_as_float(u << 16); b = __uint_as_float(u & 0xFFFF0000u); return; }
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+  a = f.x; b = f.y;
+}
+
+// shared-memory plan, computed identically on host and device
+struct PairSmem {
+  uint32_t xb, x_off, wres_off, ring_off, stg_off, bias_off, bar_off, total;
+};
+__host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int NSTG, int SW, int stream1, int stream2) {
+  const uint32_t BKC = C >= 64 ? 64 : 32, RB = BKC * 2, KCH = C / BKC, WBLK = (uint32_t)C * RB;
+  PairSmem s;
+  s.xb = ((KCH * (uint32_t)HA * RB) + 1023u) & ~1023u;
+  s.x_off = 0;
+  s.wres_off = s.x_off + NX * s.xb;
+  const uint32_t nres = (stream1 ? 0 : k * KCH) + (stream2 ? 0 : k * KCH);
+  s.ring_off = s.wres_off + nres * WBLK;
+  s.stg_off = s.ring_off + SW * WBLK;
+  s.bias_off = s.stg_off + 4u * NSTG * 32u * RB;
+  s.bar_off = s.bias_off + 2u * C * 4u;
+  s.total = s.bar_off + 8u * 64u;
+  return s;
+}
+
+template <int C, bool BF16>
+__global__ void __launch_bounds__(RP_THREADS, 1)
+resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairArgs a) {
+  constexpr int BKC = C >= 64 ? 64 : 32;       // channels per K chunk (one swizzled row)
+  constexpr uint32_t RB = BKC * 2;             // bytes per row of a chunk
+  constexpr int KCH = C / BKC;
+  constexpr uint32_t WBLK = (uint32_t)C * RB;  // one (tap, chunk) weight block
+  constexpr int KS = BKC / 16;                 // MMAs (K = 16) per chunk
+  constexpr int UPC = BKC / 8;                 // 16-byte units per chunk row
+  constexpr uint32_t TMEM_COLS = 512;
+
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const PairSmem sp = pair_smem(C, a.HA, a.k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2);
+  const int NX = a.NX, ND = a.ND, SW = a.SW;
+  const uint32_t chunk_bytes = (uint32_t)a.HA * RB;
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (base + sp.bias_off - smem_u32(smem_dyn)));
+  const uint32_t bars = base + sp.bar_off;
+  // barrier map (8 bytes each)
+  auto x_full = [&](int i) { return bars + 8u * i; };            // [4]
+  auto x_empty = [&](int i) { return bars + 8u * (4 + i); };     // [4]
+  auto t_full = [&](int i) { return bars + 8u * (8 + i); };      // [4]
+  auto d1_full = [&](int i) { return bars + 8u * (12 + i); };    // [2]
+  auto d1_empty = [&](int i) { return bars + 8u * (14 + i); };   // [2]
+  auto d2_init = [&](int i) { return bars + 8u * (16 + i); };    // [2]
+  auto d2_full = [&](int i) { return bars + 8u * (18 + i); };    // [2]
+  auto d2_empty = [&](int i) { return bars + 8u * (20 + i); };   // [2]
+  const uint32_t wres_full = bars + 8u * 22;
+  auto wr_full = [&](int i) { return bars + 8u * (24 + i); };    // [16]
+  auto wr_empty = [&](int i) { return bars + 8u * (40 + i); };   // [16]
+  const uint32_t tmem_slot = bars + 8u * 56;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bias_s[i] = i < C ? a.b1[i] : a.b2[i - C];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 2); mbar_init(t_full(i), 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(d1_full(i), 2); mbar_init(d1_empty(i), 4); mbar_init(d2_init(i), 4);
+      mbar_init(d2_full(i), 2); mbar_init(d2_empty(i), 4);
+    }
+    mbar_init(wres_full, 1);
+    for (int i = 0; i < 16; ++i) { mbar_init(wr_full(i), 1); mbar_init(wr_empty(i), 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.y) : "memory");
+  }
+  if (warp == 2 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w2) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // TMEM columns: D1[buf][mtile] at (buf*2 + mtile)*C, D2[buf][mtile] at (2*ND + buf*2 + mtile)*C
+  auto d1_col = [&](int buf, int mt) { return tmem_base + (uint32_t)((buf * 2 + mt) * C); };
+  auto d2_col = [&](int buf, int mt) { return tmem_base + (uint32_t)((2 * ND + buf * 2 + mt) * C); };
+
+  const int n_local = ((int)blockIdx.x < a.total_tiles) ? (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nblk = a.k * KCH;                                     // weight blocks per conv
+  const uint32_t w1_res = base + sp.wres_off;                     // resident conv1 blocks (if !stream1)
+  const uint32_t w2_res = base + sp.wres_off + (a.stream1 ? 0u : (uint32_t)nblk * WBLK);
+  const uint32_t ring = base + sp.ring_off;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== activation-tile producer =====
+      for (int i = 0; i < n_local; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / a.tiles_per_item, tt = tile - b * a.tiles_per_item;
+        const int xb = i % NX;
+        const uint32_t ph = (uint32_t)(i / NX) & 1u;
+        mbar_wait(x_empty(xb), ph ^ 1u);
+        mbar_expect_tx(x_full(xb), (uint32_t)KCH * chunk_bytes);
+        const int row0 = tt * a.R_out - a.p2 - a.p1;
+        const uint32_t dst = base + sp.x_off + xb * sp.xb;
+#pragma unroll
+        for (int c = 0; c < KCH; ++c)
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(dst + c * chunk_bytes + h * a.HB * RB, &maps.x, x_full(xb), c * BKC, row0 + h * a.HB, b);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ===== weight producer: resident blocks once, streamed blocks through the ring every tile =====
+      const int nres = (a.stream1 ? 0 : nblk) + (a.stream2 ? 0 : nblk);
+      if (nres > 0) {
+        mbar_expect_tx(wres_full, (uint32_t)nres * WBLK);
+        if (!a.stream1)
+          for (int j = 0; j < nblk; ++j)
+            tma_load_2d(w1_res + j * WBLK, &maps.w1, wres_full, (j % KCH) * BKC, (j / KCH) * C);
+        if (!a.stream2)
+          for (int j = 0; j < nblk; ++j)
+            tma_load_2d(w2_res + j * WBLK, &maps.w2, wres_full, (j % KCH) * BKC, (j / KCH) * C);
+      }
+      if (a.stream1 || a.stream2) {
+        int g = 0;
+        for (int i = 0; i < n_local; ++i) {
+          for (int conv = 0; conv < 2; ++conv) {
+            if (!(conv == 0 ? a.stream1 : a.stream2)) continue;
+            const CUtensorMap* wm = conv == 0 ? &maps.w1 : &maps.w2;
+            for (int j = 0; j < nblk; ++j, ++g) {
+              const int slot = g % SW;
+              const uint32_t ph = (uint32_t)(g / SW) & 1u;
+              mbar_wait(wr_empty(slot), ph ^ 1u);
+              mbar_expect_tx(wr_full(slot), WBLK);
+              tma_load_2d(ring + slot * WBLK, wm, wr_full(slot), (j % KCH) * BKC, (j / KCH) * C);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===== MMA issuers: warp 1 owns M-tile 0, warp 3 owns M-tile 1 (separate accumulators, separate
+    // schedulers).  At N = C <= 128 one thread cannot issue tcgen05.mma fast enough to keep the tensor
+    // pipe busy (measured ~100 clk per instruction with a single issuer), so the issue stream is split
+    // and kept branch-free: the warp stays converged, one elected lane issues. =====
+    const int mt = warp == 1 ? 0 : 1;
+    if (elect_one()) {
+      if (!a.stream1 || !a.stream2) mbar_wait(wres_full, 0);
+      int slot = 0;            // weight ring position (streamed convolutions, in-order mode only)
+      uint32_t slot_ph = 0;
+      const uint64_t chunk_step = (uint64_t)(chunk_bytes >> 4);
+      const uint32_t idesc = a.idesc;
+      const int k = a.k;
+      // one convolution of one M-tile: k taps x KCH chunks x KS instructions into accumulator `tacc`
+      auto run_conv = [&](uint32_t tacc, uint64_t da_tap, uint64_t tap_step, uint32_t w_res, bool streamed, uint32_t acc) {
+        if (!streamed) {
+          uint64_t dw = make_smem_desc<BKC>(w_res);
+          for (int tap = 0; tap < k; ++tap, da_tap += tap_step) {
+#pragma unroll
+            for (int c = 0; c < KCH; ++c, dw += (uint64_t)(WBLK >> 4)) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                acc = 1u;
+              }
+            }
+          }
+        } else {
+          for (int tap = 0; tap < k; ++tap, da_tap += tap_step) {
+#pragma unroll
+            for (int c = 0; c < KCH; ++c) {
+              mbar_wait(wr_full(slot), slot_ph);
+              tc_fence_after();
+              const uint64_t dw = make_smem_desc<BKC>(ring + slot * WBLK);
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                acc = 1u;
+              }
+              tc_commit(wr_empty(slot));
+              if (++slot == SW) { slot = 0; slot_ph ^= 1u; }
+            }
+          }
+        }
+      };
+      auto issue1 = [&](int i) {
+        const int xb = i % NX, db = i % ND;
+        mbar_wait(x_full(xb), (uint32_t)(i / NX) & 1u);
+        mbar_wait(d1_empty(db), ((uint32_t)(i / ND) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc<BKC>(base + sp.x_off + xb * sp.xb + (uint32_t)(mt * 128) * RB);
+        run_conv(d1_col(db, mt), da, (uint64_t)((uint32_t)a.dil * RB >> 4), w1_res, a.stream1 != 0, 0u);
+        tc_commit(d1_full(db));
+      };
+      auto issue2 = [&](int i) {
+        const int xb = i % NX, db = i % ND;
+        mbar_wait(t_full(xb), (uint32_t)(i / NX) & 1u);
+        mbar_wait(d2_init(db), (uint32_t)(i / ND) & 1u);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc<BKC>(base + sp.x_off + xb * sp.xb + (uint32_t)(mt * 128) * RB);
+        run_conv(d2_col(db, mt), da, (uint64_t)(RB >> 4), w2_res, a.stream2 != 0, 1u);
+        tc_commit(x_empty(xb));
+        tc_commit(d2_full(db));
+      };
+      if (a.pipelined) {
+        // stage 1 of tile i+1 is issued before stage 2 of tile i: the tensor pipe works on it while
+        // warpgroup 0 converts tile i's accumulator into the stage-2 operand
+        if (n_local > 0) issue1(0);
+        for (int i = 0; i < n_local; ++i) {
+          if (i + 1 < n_local) issue1(i + 1);
+          issue2(i);
+        }
+      } else {
+        for (int i = 0; i < n_local; ++i) { issue1(i); issue2(i); }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ===== warpgroup 0: seed D2 with residual + bias2, then epilogue 1 (D1 -> stage-2 operand) =====
+    const int q = warp & 3;
+    const float slope = a.slope, inv_slope = a.inv_slope;
+    for (int i = 0; i < n_local; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int b = tile / a.tiles_per_item, tt = tile - b * a.tiles_per_item;
+      const int xb = i % NX, db = i % ND;
+      const int o0 = tt * a.R_out;
+      int len_b = a.L;
+      if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
+      const uint32_t xa = base + sp.x_off + xb * sp.xb;
+      mbar_wait(x_full(xb), (uint32_t)(i / NX) & 1u);
+      mbar_wait(d2_empty(db), ((uint32_t)(i / ND) & 1u) ^ 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t arow = (uint32_t)(mt * 128 + q * 32 + lane + a.p1 + a.p2);
+        const uint32_t swz = (BKC == 64) ? (arow & 7u) : ((arow >> 1) & 3u);
+        const uint32_t rbase = xa + arow * RB;
+        const uint32_t tcol = d2_col(db, mt) + (uint32_t(q * 32) << 16);
+#pragma unroll
+        for (int cc = 0; cc < C / 16; ++cc) {
+          const int c = (cc * 2) / UPC, u = (cc * 2) % UPC;
+          const uint4 t0 = lds128(rbase + c * chunk_bytes + (((uint32_t)u ^ swz) << 4));
+          const uint4 t1 = lds128(rbase + c * chunk_bytes + (((uint32_t)(u + 1) ^ swz) << 4));
+          const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          uint32_t r[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v0, v1;
+            unpack2<BF16>(w[e], v0, v1);
+            v0 = (v0 < 0.f ? v0 * inv_slope : v0) + bias_s[C + cc * 16 + 2 * e];
+            v1 = (v1 < 0.f ? v1 * inv_slope : v1) + bias_s[C + cc * 16 + 2 * e + 1];
+            r[2 * e] = __float_as_uint(v0); r[2 * e + 1] = __float_as_uint(v1);
+          }
+          tc_st16(tcol + (uint32_t)(cc * 16), r);
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_init(db));
+
+      mbar_wait(d1_full(db), (uint32_t)(i / ND) & 1u);
+      tc_fence_after();
+      wg_sync(1);   // every warp of the group has read its residual rows: the tile may be overwritten
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t m = (uint32_t)(mt * 128 + q * 32 + lane);
+        const int trow = o0 - a.p2 + (int)m;
+        const bool valid = trow >= 0 && trow < len_b;
+        const uint32_t swz = (BKC == 64) ? (m & 7u) : ((m >> 1) & 3u);
+        const uint32_t rbase = xa + m * RB;
+        const uint32_t tcol = d1_col(db, mt) + (uint32_t(q * 32) << 16);
+#pragma unroll
+        for (int cc = 0; cc < C / 16; ++cc) {
+          uint32_t r[16];
+          tc_ld16(tcol + (uint32_t)(cc * 16), r);
+          tc_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float t = __uint_as_float(r[e]) + bias_s[cc * 16 + e];
+            v[e] = valid ? fmaxf(t, t * slope) : 0.f;
+          }
+          const int c = (cc * 2) / UPC, u = (cc * 2) % UPC;
+          sts128(rbase + c * chunk_bytes + (((uint32_t)u ^ swz) << 4),
+                 make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+          sts128(rbase + c * chunk_bytes + (((uint32_t)(u + 1) ^ swz) << 4),
+                 make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(d1_empty(db)); mbar_arrive(t_full(xb)); }
+    }
+  } else if (warp >= 8) {
+    // ===== warpgroup 1: epilogue 2 (D2 -> other branches, scale, mask, activation -> TMA store) =====
+    const int q = warp & 3;
+    const uint32_t stg0 = base + sp.stg_off + (uint32_t)q * a.NSTG * 32u * RB;
+    const uint32_t swz = (BKC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+    const float scale = a.out_scale, aslope = a.out_slope_eff;
+    const bool has_res = a.res2 != nullptr || a.res3 != nullptr;
+    int nst = 0;
+    for (int i = 0; i < n_local; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int b = tile / a.tiles_per_item, tt = tile - b * a.tiles_per_item;
+      const int db = i % ND;
+      const int o0 = tt * a.R_out;
+      int len_b = a.L;
+      if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
+      mbar_wait(d2_full(db), (uint32_t)(i / ND) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int o = mt * 128 + q * 32 + lane;
+        const int grow = o0 + o;
+        const bool masked = grow >= len_b;
+        const int rows_here = min(32, a.R_out - (mt * 128 + q * 32));   // warp-uniform
+        const uint32_t tcol = d2_col(db, mt) + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < KCH; ++c) {
+          const uint32_t stg = stg0 + (uint32_t)(nst % a.NSTG) * 32u * RB;
+          ++nst;
+          if (lane == 0) { if (a.NSTG > 1) bulk_wait_read1(); else bulk_wait_read0(); }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < BKC / 16; ++cc) {
+            const int c0 = c * BKC + cc * 16;
+            uint32_t r[16];
+            tc_ld16(tcol + (uint32_t)c0, r);
+            tc_wait_ld();
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+            if (has_res && o < a.R_out && grow < a.L) {
+              const long long rrow = (long long)b * a.L + grow;
+              if (a.res2 != nullptr) {
+                const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res2) + rrow * a.res2_ld + c0);
+                const uint4 t0 = __ldg(p), t1 = __ldg(p + 1);
+                unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+                unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+                unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+                unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+              }
+              if (a.res3 != nullptr) {
+                const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res3) + rrow * a.res3_ld + c0);
+                const uint4 t0 = __ldg(p), t1 = __ldg(p + 1);
+                unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+                unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+                unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+                unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float t = masked ? 0.f : v[e] * scale;
+              v[e] = fmaxf(t, t * aslope);
+            }
+            const uint32_t o_lo = stg + (uint32_t)lane * RB + ((((uint32_t)(2 * cc)) ^ swz) << 4);
+            const uint32_t o_hi = stg + (uint32_t)lane * RB + ((((uint32_t)(2 * cc + 1)) ^ swz) << 4);
+            sts128(o_lo, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+            sts128(o_hi, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (rows_here >= 32) tma_store_3d(&maps.y, stg, c * BKC, o0 + mt * 128 + q * 32, b);
+            else if (rows_here > 0) tma_store_3d(&maps.y_tail, stg, c * BKC, o0 + mt * 128 + q * 32, b);
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty(db));
+    }
+    if (lane == 0) bulk_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int C, bool BF16>
+static int launch_pair(const PairMaps& maps, const PairArgs& a, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASB_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = num_sms();
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  resblock_pair_kernel<C, BF16><<<grid, RP_THREADS, smem, st>>>(maps, a);
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace asb
+
+extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* stream) {
+  using namespace asb;
+  ASB_REQUIRE(p != nullptr, AS_ERR_SHAPE, "as_hifigan_resblock_pair: null params");
+  ASB_REQUIRE(p->dtype == AS_F16 || p->dtype == AS_BF16, AS_ERR_DTYPE, "as_hifigan_resblock_pair: dtype must be f16 or bf16");
+  ASB_REQUIRE(p->C == 32 || p->C == 64 || p->C == 128, AS_ERR_SHAPE, "as_hifigan_resblock_pair: C=%d not in {32, 64, 128}", p->C);
+  ASB_REQUIRE(p->B > 0 && p->L > 0, AS_ERR_SHAPE, "as_hifigan_resblock_pair: non-positive dimension");
+  ASB_REQUIRE(p->k >= 1 && (p->k & 1) == 1 && p->k <= 15 && p->dil >= 1 && (p->k - 1) * p->dil <= 64, AS_ERR_SHAPE,
+              "as_hifigan_resblock_pair: k=%d dil=%d unsupported (odd k <= 15, (k-1)*dil <= 64)", p->k, p->dil);
+  ASB_REQUIRE(p->x && p->w1 && p->w2 && p->b1 && p->b2 && p->y, AS_ERR_SHAPE, "as_hifigan_resblock_pair: null pointer");
+  ASB_REQUIRE(p->slope > 0.f && p->slope <= 1.f, AS_ERR_SHAPE, "as_hifigan_resblock_pair: slope must be in (0, 1]");
+  ASB_REQUIRE(p->out_act == AS_ACT_NONE || (p->out_act == AS_ACT_LRELU && p->out_slope <= 1.f), AS_ERR_SHAPE,
+              "as_hifigan_resblock_pair: out_act must be none or LeakyReLU with slope <= 1");
+  auto aligned = [](const void* ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0; };
+  ASB_REQUIRE(aligned(p->x, p->x_ld) && aligned(p->y, p->y_ld) && p->x_ld >= p->C && p->y_ld >= p->C, AS_ERR_ALIGN,
+              "as_hifigan_resblock_pair: x / y must be 16-byte aligned with row strides that are multiples of 8");
+  ASB_REQUIRE((reinterpret_cast<uintptr_t>(p->w1) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w2) & 15) == 0, AS_ERR_ALIGN,
+              "as_hifigan_resblock_pair: weights must be 16-byte aligned");
+  ASB_REQUIRE((p->res2 == nullptr || aligned(p->res2, p->res2_ld)) && (p->res3 == nullptr || aligned(p->res3, p->res3_ld)),
+              AS_ERR_ALIGN, "as_hifigan_resblock_pair: res2 / res3 alignment");
+  int rc = check_arch();
+  if (rc != AS_OK) return rc;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return AS_ERR_CUDA;
+
+  const int C = p->C, k = p->k;
+  const int BKC = C >= 64 ? 64 : 32, KCH = C / BKC;
+  const size_t RB = BKC * 2, WBLK = (size_t)C * RB;
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = p->B; a.L = p->L; a.k = k; a.dil = p->dil;
+  a.p1 = (k - 1) * p->dil / 2; a.p2 = (k - 1) / 2;
+  a.R_out = 256 - (k - 1);
+  a.HA = (256 + (k - 1) * p->dil + 15) / 16 * 16;
+  a.HB = a.HA / 2;
+  a.tail_rows = a.R_out - 224;
+  a.tiles_per_item = (p->L + a.R_out - 1) / a.R_out;
+  a.total_tiles = p->B * a.tiles_per_item;
+  a.ND = C <= 64 ? 2 : 1;
+  // shared-memory plan: weights resident when they fit next to two activation buffers, else conv1
+  // (then both) streamed through a ring; remaining room goes to a 2nd staging buffer, then more buffers
+  const size_t cap = 227 * 1024 - 1024;
+  const size_t nblk = (size_t)k * KCH;
+  int best_found = 0;
+  for (int mode = 0; mode < 3 && !best_found; ++mode) {   // 0: resident, 1: conv1 streamed, 2: both streamed
+    a.stream1 = mode >= 1; a.stream2 = mode >= 2;
+    for (int nx = 2; nx >= 1 && !best_found; --nx) {
+      if (mode == 0 && nx == 1) continue;                 // prefer streaming conv1 over a single buffer
+      a.NX = nx; a.NSTG = 1;
+      a.SW = mode == 0 ? 0 : 3;
+      if (pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2).total > cap) continue;
+      best_found = 1;
+      if (mode > 0) {
+        const int want = (int)((a.stream1 ? nblk : 0) + (a.stream2 ? nblk : 0));
+        while (a.SW < 16 && a.SW < want && pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW + 1, a.stream1, a.stream2).total <= cap) ++a.SW;
+      }
+      if (pair_smem(C, a.HA, k, a.NX, 2, a.SW, a.stream1, a.stream2).total <= cap) a.NSTG = 2;
+      while (a.NX < 3 && mode == 0 && pair_smem(C, a.HA, k, a.NX + 1, a.NSTG, a.SW, a.stream1, a.stream2).total <= cap) ++a.NX;
+    }
+  }
+  if (!best_found) {
+    a.stream1 = a.stream2 = 1; a.NX = 1; a.NSTG = 1; a.SW = 2;
+    ASB_REQUIRE(pair_smem(C, a.HA, k, 1, 1, 2, 1, 1).total <= cap, AS_ERR_SHAPE, "as_hifigan_resblock_pair: tile does not fit in shared memory");
+  }
+  // tuning overrides (tools/prof_pair.py)
+  a.NX = env_int("ASB_PAIR_NX", a.NX); a.NSTG = env_int("ASB_PAIR_NSTG", a.NSTG); a.SW = env_int("ASB_PAIR_SW", a.SW);
+  a.pipelined = (a.ND == 2 && a.NX >= 2 && !a.stream1 && !a.stream2) ? 1 : 0;
+  a.pipelined = env_int("ASB_PAIR_PIPE", a.pipelined);
+  if (a.stream1 || a.stream2 || a.ND < 2 || a.NX < 2) a.pipelined = 0;
+  const PairSmem sp = pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2);
+  ASB_REQUIRE(sp.total <= cap && a.NX >= 1 && a.NX <= 4 && a.NSTG >= 1 && a.NSTG <= 2 && a.SW <= 16 &&
+                  (!(a.stream1 || a.stream2) || a.SW >= 2),
+              AS_ERR_SHAPE, "as_hifigan_resblock_pair: invalid shared-memory plan (%u bytes)", sp.total);
+
+  const uint32_t fmt = (p->dtype == AS_BF16) ? 1u : 0u;
+  a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(C >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  a.b1 = p->b1; a.b2 = p->b2;
+  a.res2 = p->res2; a.res2_ld = p->res2_ld; a.res3 = p->res3; a.res3_ld = p->res3_ld;
+  a.slope = p->slope; a.inv_slope = 1.0f / p->slope;
+  a.out_scale = p->out_scale;
+  a.out_slope_eff = p->out_act == AS_ACT_LRELU ? p->out_slope : 1.0f;
+  a.lens = p->lens;
+
+  const CUtensorMapDataType dt = p->dtype == AS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  PairMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  auto mk3 = [&](CUtensorMap* m, const void* ptr, long long ld, int rows) -> bool {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)p->L, (cuuint64_t)p->B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * p->L};
+    cuuint32_t box[3] = {(cuuint32_t)BKC, (cuuint32_t)rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  auto mkw = [&](CUtensorMap* m, const void* ptr) -> bool {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)k * C};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BKC, (cuuint32_t)C};
+    cuuint32_t es[2] = {1, 1};
+    return enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  bool ok = mk3(&maps.x, p->x, p->x_ld, a.HB) && mkw(&maps.w1, p->w1) && mkw(&maps.w2, p->w2) &&
+            mk3(&maps.y, p->y, p->y_ld, 32) && mk3(&maps.y_tail, p->y, p->y_ld, a.tail_rows);
+  ASB_REQUIRE(ok, AS_ERR_CUDA, "as_hifigan_resblock_pair: cuTensorMapEncodeTiled failed");
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem = sp.total + 1024;
+  const bool bf = p->dtype == AS_BF16;
+  if (C == 32) return bf ? launch_pair<32, true>(maps, a, smem, st) : launch_pair<32, false>(maps, a, smem, st);
+  if (C == 64) return bf ? launch_pair<64, true>(maps, a, smem, st) : launch_pair<64, false>(maps, a, smem, st);
+  return bf ? launch_pair<128, true>(maps, a, smem, st) : launch_pair<128, false>(maps, a, smem, st);
+}

@@ -184,6 +184,48 @@ def conv(x: torch.Tensor, pw: PackedConv, *, out_shape=None, use_bias: bool = Tr
     return raw_t, act_t
 
 
+def resblock_pair(xa: torch.Tensor, c1: PackedConv, c2: PackedConv, k: int, dil: int, *, slope: float,
+                  res2: Optional[torch.Tensor] = None, res3: Optional[torch.Tensor] = None, scale: float = 1.0,
+                  out_act: int = ACT_NONE, out_slope: float = 1.0, lens: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run ``as_hifigan_resblock_pair`` on the ACTIVATED residual stream ``xa = leaky_relu(x, slope)``.
+
+    ``xa``: ``[B, L, C]`` 16-bit channels-last, ``C`` in {32, 64, 128}; ``c1`` / ``c2``: the packed
+    ``Conv1d(C, C, k, dilation=dil)`` / ``Conv1d(C, C, k)`` of one ResBlock1 iteration.  Returns
+    ``out_act((conv2(lrelu(conv1(xa))) + x + res2 + res3) * scale)`` as a 16-bit ``[B, L, C]`` tensor.
+    """
+    _require_cuda(xa, "resblock_pair")
+    lib = _lib.load()
+    B, L, C_ = xa.shape
+    for pw in (c1, c2):
+        if (pw.Cin, pw.Cout, pw.CinP, pw.CoutP, pw.ntaps) != (C_, C_, C_, C_, k) or pw.w.dtype != xa.dtype or pw.bias is None:
+            raise _lib.AsError("resblock_pair: weights must be packed [k][C][C] in the activation dtype, with bias")
+    if out is None:
+        out = torch.empty(B, L, C_, dtype=xa.dtype, device=xa.device)
+    p = _lib.ResblockPairParams()
+    p.x = xa.data_ptr(); p.x_ld = _rows_ld(xa, "resblock_pair.x"); p.dtype = dtype_code(xa.dtype)
+    p.B, p.L, p.C, p.k, p.dil = B, L, C_, int(k), int(dil)
+    p.w1 = c1.w.data_ptr(); p.b1 = c1.bias.data_ptr(); p.w2 = c2.w.data_ptr(); p.b2 = c2.bias.data_ptr()
+    p.slope = float(slope)
+    for name, r in (("res2", res2), ("res3", res3)):
+        if r is not None:
+            if r.dtype != xa.dtype or r.shape != xa.shape:
+                raise _lib.AsError(f"resblock_pair: {name} must match x in shape and dtype")
+            setattr(p, name, r.data_ptr())
+            setattr(p, name + "_ld", _rows_ld(r, "resblock_pair." + name))
+    p.out_scale = float(scale); p.out_act = int(out_act); p.out_slope = float(out_slope)
+    p.y = out.data_ptr(); p.y_ld = _rows_ld(out, "resblock_pair.out")
+    if lens is not None:
+        if lens.dtype != torch.int32:
+            raise _lib.AsError("resblock_pair: lens must be int32")
+        p.lens = lens.data_ptr()
+    with torch.cuda.device(xa.device):
+        rc = lib.as_hifigan_resblock_pair(C.byref(p), _stream(xa))
+    _lib.check(rc, "as_hifigan_resblock_pair")
+    _count()
+    return out
+
+
 # tap tables -------------------------------------------------------------------------------------
 def taps_1d(k: int, dilation: int = 1, padding: Optional[int] = None):
     """Conv1d taps: input index = t + j*dilation - padding ('same' padding by default)."""

@@ -21,6 +21,7 @@ length (at x10/x50/x150/x300 rates), which makes the batch equal to batch-1 runs
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -30,6 +31,7 @@ from torch.nn.utils import remove_weight_norm, weight_norm
 from . import ops
 
 LRELU_SLOPE = 0.1
+FUSED_PAIR_CHANNELS = (32, 64, 128)      # stages run by as_hifigan_resblock_pair (one launch per conv pair)
 
 
 def get_padding(kernel_size: int, dilation: int = 1) -> int:
@@ -116,6 +118,7 @@ class Generator(nn.Module):
         post.weight.data.normal_(0.0, 0.01)
         self.conv_post = weight_norm(post)
         self.compute_dtype = torch.bfloat16
+        self.fuse_pairs = os.environ.get("ASB_NO_FUSED_PAIRS") is None
         self._plan = None
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate_plan())
 
@@ -188,6 +191,35 @@ class Generator(nn.Module):
             u = self.h.upsample_rates[i]
             up = plan["ups"][i]
             cout = up.Cout // u
+            last_stage = i == n_up - 1
+            # the activation that follows the stage: lrelu(0.1) before ups[i+1], but the default
+            # slope 0.01 before conv_post (vocoder.py:112 calls F.leaky_relu without a slope)
+            next_slope = 0.01 if last_stage else LRELU_SLOPE
+            if cout in FUSED_PAIR_CHANNELS and self.fuse_pairs and self.num_kernels <= 3:
+                # fused path: the residual stream lives in HBM in activated form only; one launch per
+                # (conv1, conv2) pair, the three MRF branches are independent until the last launch
+                _, xa = ops.conv(a, up, act_out=dt, act=ops.ACT_LRELU, slope=LRELU_SLOPE, lens=lens)
+                L = L * u
+                xa = xa.view(B, L, cout)
+                if lens is not None:
+                    lens = lens * u
+                done = []          # raw outputs of finished branches
+                for j in range(self.num_kernels):
+                    blk = self.resblocks[i * self.num_kernels + j]
+                    c1s, c2s = plan["res"][i * self.num_kernels + j]
+                    ra = xa
+                    nconv = len(c1s)
+                    for m in range(nconv):
+                        kw = dict(slope=LRELU_SLOPE, lens=lens)
+                        if m < nconv - 1:
+                            kw.update(out_act=ops.ACT_LRELU, out_slope=LRELU_SLOPE)
+                        elif j == self.num_kernels - 1:
+                            kw.update(res2=done[0] if len(done) > 0 else None, res3=done[1] if len(done) > 1 else None,
+                                      scale=1.0 / self.num_kernels, out_act=ops.ACT_LRELU, out_slope=next_slope)
+                        ra = ops.resblock_pair(ra, c1s[m], c2s[m], blk.kernel_size, blk.dilation[m], **kw)
+                    done.append(ra)
+                a = done[-1]
+                continue
             # ups[i]: rows of u*Cout -> viewed as [B, L*u, Cout]; keep x (residual) and lrelu(x)
             xr, xa = ops.conv(a, up, raw=dt, act_out=dt, act=ops.ACT_LRELU, slope=LRELU_SLOPE, lens=lens)
             L = L * u
@@ -195,10 +227,6 @@ class Generator(nn.Module):
             xa = xa.view(B, L, cout)
             if lens is not None:
                 lens = lens * u
-            last_stage = i == n_up - 1
-            # the activation that follows the stage: lrelu(0.1) before ups[i+1], but the default
-            # slope 0.01 before conv_post (vocoder.py:112 calls F.leaky_relu without a slope)
-            next_slope = 0.01 if last_stage else LRELU_SLOPE
             xs = None          # running sum of finished MRF branches (residual stream dtype)
             for j in range(self.num_kernels):
                 c1s, c2s = plan["res"][i * self.num_kernels + j]

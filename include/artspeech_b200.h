@@ -115,6 +115,47 @@ typedef struct as_conv_params {
 int32_t as_conv_tile_n(int32_t Cout);
 int as_conv_igemm(const as_conv_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused HiFi-GAN ResBlock1 pair — replaces one iteration of Vocoder/vocoder.py:36-41
+ *     xt = c1(leaky_relu(x, slope)); xt = c2(leaky_relu(xt, slope)); x = xt + x
+ * (c1: Conv1d(C, C, k, dilation=dil), c2: Conv1d(C, C, k), both 'same'-padded) in one launch; the
+ * intermediate stays in shared memory / TMEM.  The residual stream is carried in ACTIVATED form:
+ *
+ *   x        [B, L, C] 16-bit channels-last holds a = leaky_relu(x_raw, slope); rows >= lens[b] are 0
+ *   x_raw    = a < 0 ? a / slope : a
+ *   t        = leaky_relu(conv1(a) + b1, slope), zero outside [0, lens[b])      (16-bit operand)
+ *   v        = (conv2(t) + b2 + x_raw + res2 + res3) * out_scale ; v = 0 for rows >= lens[b]
+ *   y        = out_act == AS_ACT_LRELU ? leaky_relu(v, out_slope) : v           (16-bit, [B, L, C])
+ *
+ * res2 / res3 (optional, 16-bit, raw) are the finished MRF branches summed by the last pair of a
+ * stage (vocoder.py:105-111, with out_scale = 1 / num_kernels).
+ * w1 / w2: packed [k][C][C] (tap, cout, cin) K-major like as_conv_igemm; C in {32, 64, 128};
+ * k odd <= 15; (k-1)*dil <= 64; fp32 accumulation; 0 < slope <= 1.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct as_resblock_pair_params {
+  const void* x;
+  int64_t x_ld;
+  int32_t dtype; /* AS_F16 or AS_BF16: x, w1, w2, res2, res3, y */
+  int32_t B, L, C, k, dil;
+  const void* w1;
+  const float* b1; /* [C] fp32 */
+  const void* w2;
+  const float* b2;
+  float slope;
+  const void* res2; /* or NULL */
+  int64_t res2_ld;
+  const void* res3; /* or NULL */
+  int64_t res3_ld;
+  float out_scale;
+  int32_t out_act; /* AS_ACT_NONE or AS_ACT_LRELU */
+  float out_slope;
+  void* y;
+  int64_t y_ld;
+  const int32_t* lens; /* device [B] or NULL */
+} as_resblock_pair_params;
+
+int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * Memory-bound / small kernels.  Unless stated otherwise `x` may be any as_dtype and is addressed

@@ -65,6 +65,28 @@ def conv(x, pw, *, out_shape=None, use_bias=True, res1=None, res2=None, scale=1.
 
 
 
+def resblock_pair(xa, c1, c2, k, dil, *, slope, res2=None, res3=None, scale=1.0, out_act=ops.ACT_NONE,
+                  out_slope=1.0, lens=None, out=None):
+    """Contract of as_hifigan_resblock_pair (include/artspeech_b200.h): the stream is carried activated."""
+    dt = xa.dtype
+    a = xa.float()
+    x_raw = torch.where(a < 0, a * (1.0 / slope), a)
+    _, t = conv(xa, c1, act_out=dt, act=ops.ACT_LRELU, slope=slope, lens=lens)       # 16-bit operand of conv2
+    v, _ = conv(t, c2, raw=torch.float32)
+    v = v + x_raw
+    for r in (res2, res3):
+        if r is not None:
+            v = v + r.float()
+    v = v * scale
+    if lens is not None:
+        v = v * (torch.arange(v.shape[1])[None, :] < lens.long()[:, None])[:, :, None]
+    y = _ACT[out_act](v, out_slope).to(dt)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
 def _mask_rows(y, lens, T):
     if lens is None:
         return y
@@ -319,7 +341,7 @@ def to_channels_first(src, out_dtype, lens=None, sub=None, mul=None):
     return y.transpose(1, 2).to(out_dtype).contiguous()
 
 
-SIM_FUNCS = ["conv", "embed", "layernorm", "relpos_attention", "conformer_attention", "instnorm_stats",
+SIM_FUNCS = ["conv", "resblock_pair", "embed", "layernorm", "relpos_attention", "conformer_attention", "instnorm_stats",
              "adain_apply", "repeat_rows", "length_regulate", "conv_small", "dwconv", "avgpool",
              "affine_act_maxpool", "global_avgpool", "bilstm", "lstm_onestep", "log_norm",
              "to_channels_last", "to_channels_first"]

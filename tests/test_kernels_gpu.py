@@ -52,6 +52,38 @@ def test_conv_igemm_1d(shape, dt):
     _close(act, ref_act, 1e-2 if dt == torch.bfloat16 else 2e-3, "act")
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 700, 64, 3, 1), (2, 1000, 64, 7, 3), (1, 1500, 64, 11, 5), (3, 333, 32, 3, 5),
+                                   (2, 2000, 32, 11, 5), (1, 900, 32, 7, 1), (2, 600, 128, 3, 3), (1, 800, 128, 7, 5),
+                                   (1, 700, 128, 11, 5), (4, 100, 64, 7, 5), (1, 246, 32, 11, 1), (1, 247, 64, 11, 3)])
+@pytest.mark.parametrize("variant", ["mid", "branch_end", "stage_end"])
+def test_resblock_pair(shape, variant, dt):
+    """as_hifigan_resblock_pair vs its contract model (Vocoder/vocoder.py:35-42 with the activated stream)."""
+    B, L, C, k, dil = shape
+    torch.manual_seed(2)
+    x_raw = torch.randn(B, L, C)
+    lens = _lens(B, L)
+    x_raw = x_raw * (torch.arange(L)[None, :] < lens[:, None])[:, :, None]
+    xa = torch.where(x_raw > 0, x_raw, 0.1 * x_raw).to(dt)
+    w1 = torch.randn(k, C, C) / (C * k) ** 0.5
+    w2 = torch.randn(k, C, C) / (C * k) ** 0.5
+    b1, b2 = torch.randn(C) * 0.1, torch.randn(C) * 0.1
+    kw = dict(slope=0.1)
+    if variant == "mid":
+        kw.update(out_act=ops.ACT_LRELU, out_slope=0.1)
+    elif variant == "stage_end":
+        kw.update(res2=torch.randn(B, L, C).to(dt), res3=torch.randn(B, L, C).to(dt), scale=1.0 / 3,
+                  out_act=ops.ACT_LRELU, out_slope=0.01)
+    packs = {}
+    for dev in ("cpu", DEV):
+        packs[dev] = (ops.pack_conv(w1, b1, ops.taps_1d(k, dil), dt, dev), ops.pack_conv(w2, b2, ops.taps_1d(k, 1), dt, dev))
+    ref = sim.resblock_pair(xa, *packs["cpu"], k, dil, lens=lens, **kw)
+    kw_g = {n: (v.to(DEV) if torch.is_tensor(v) else v) for n, v in kw.items()}
+    out = ops.resblock_pair(xa.to(DEV), *packs[DEV], k, dil, lens=lens.to(DEV), **kw_g)
+    _close(out, ref, 1.2e-2 if dt == torch.bfloat16 else 2e-3, f"pair {shape} {variant}")
+    assert torch.count_nonzero(out.cpu()[0, lens[0]:]) == 0 and torch.count_nonzero(out.cpu()[-1, lens[-1]:]) == 0
+
+
 @pytest.mark.parametrize("shape", [(2, 70, 80, 64, 64, 3, 3), (1, 33, 40, 128, 128, 3, 3), (2, 50, 10, 64, 128, 3, 3),
                                    (1, 15, 5, 512, 512, 5, 5)])
 def test_conv_igemm_2d(shape):

@@ -248,6 +248,149 @@ conformer_attention_kernel(const float* __restrict__ q, const float* __restrict_
     stany(out, ((long long)b * T + a) * out_ld + h * D + lane + 32 * c, acc[c] * inv, odt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled conformer attention (the per-query kernel above re-reads K / pos / V from L1/L2 for every
+// query with one row per lane: 545 us for B=16, T=240 under ncu).  One CTA per (b, h, 32 queries):
+// K, pos and V stream once through a shared 32-row tile; content scores S = (Q+u) K^T and position
+// scores M = (Q+v) P^T are two small GEMMs (lane <-> key, 4 queries per warp), the Transformer-XL
+// relative shift (attention.py:105-113) is a gather from M: out[a][j] = M[i2][jj-1] with
+// (i2, jj) = divmod((a+1)*L + j, L+1), zero when jj == 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int CT_QT = 32;       // queries per CTA
+constexpr int CT_WARPS = 8;     // 4 queries per warp
+
+template <int D>
+__global__ void __launch_bounds__(CT_WARPS * 32)
+conformer_attention_tiled_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                 const float* __restrict__ v, long long ld, const float* __restrict__ pos,
+                                 const float* __restrict__ ub, const float* __restrict__ vb, int T, int H,
+                                 const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  constexpr int KS = D + 4;     // padded row stride of the key tile (float4-aligned, conflict-free)
+  constexpr int QPW = CT_QT / CT_WARPS;
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, a0 = blockIdx.x * CT_QT;
+  const int len = lens ? min(lens[b], T) : T;
+  const int Tpad = (T + 31) & ~31;
+  float* Qu = sm;                           // [QT][D]      q + u
+  float* Qv = Qu + CT_QT * D;               // [QT+1][D]    q + v (rows a0 .. a0+QT)
+  float* KT = Qv + (CT_QT + 1) * D;         // [32][KS]
+  float* S = KT + 32 * KS;                  // [QT][Tpad]
+  float* Mx = S + CT_QT * Tpad;             // [QT+1][Tpad]
+  const int HD = H * D;
+  if (a0 >= len) {
+    for (int i = threadIdx.x; i < CT_QT * D; i += blockDim.x) {
+      const int r = a0 + i / D;
+      if (r < T) stany(out, ((long long)b * T + r) * out_ld + h * D + (i % D), 0.f, odt);
+    }
+    return;
+  }
+  const float* qb = q + (long long)b * T * ld + h * D;
+  const float* kb = k + (long long)b * T * ld + h * D;
+  const float* vbase = v + (long long)b * T * ld + h * D;
+  for (int i = threadIdx.x; i < (CT_QT + 1) * D; i += blockDim.x) {
+    const int r = i / D, d = i - r * D, a = a0 + r;
+    const float qa = a < len ? qb[(long long)a * ld + d] : 0.f;
+    if (r < CT_QT) Qu[i] = qa + ub[h * D + d];
+    Qv[i] = qa + vb[h * D + d];
+  }
+  const int L = len;
+  auto load_tile = [&](const float* src, long long stride, int j0) {
+    for (int i = threadIdx.x; i < 32 * (D / 4); i += blockDim.x) {
+      const int r = i / (D / 4), c = i - r * (D / 4);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + r < L) t = *reinterpret_cast<const float4*>(src + (long long)(j0 + r) * stride + 4 * c);
+      *reinterpret_cast<float4*>(KT + r * KS + 4 * c) = t;
+    }
+  };
+  // rows of `Qm` (nrows of them, this warp's share) dotted with the 32 keys of the tile
+  auto dot_rows = [&](const float* Qm, int r0, int nrows, float* dst, int j0) {
+    float acc[QPW + 1];
+#pragma unroll
+    for (int i = 0; i < QPW + 1; ++i) acc[i] = 0.f;
+    const float* kr = KT + lane * KS;
+#pragma unroll 4
+    for (int d = 0; d < D; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+#pragma unroll
+      for (int i = 0; i < QPW + 1; ++i) {
+        if (i < nrows) {
+          const float4 qq = *reinterpret_cast<const float4*>(Qm + (r0 + i) * D + d);
+          acc[i] += qq.x * kk.x + qq.y * kk.y + qq.z * kk.z + qq.w * kk.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < QPW + 1; ++i)
+      if (i < nrows) dst[(r0 + i) * Tpad + j0 + lane] = acc[i];
+  };
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    __syncthreads();
+    load_tile(kb, ld, j0);
+    __syncthreads();
+    dot_rows(Qu, warp * QPW, QPW, S, j0);
+    __syncthreads();
+    load_tile(pos + h * D, HD, j0);
+    __syncthreads();
+    // warp 7 also takes the extra row QT (query a0+QT, needed by the shift of the tile's last query)
+    dot_rows(Qv, warp * QPW, warp == CT_WARPS - 1 ? QPW + 1 : QPW, Mx, j0);
+  }
+  __syncthreads();
+  const float inv_sqrt = rsqrtf((float)HD);
+  float inv_sum[QPW];
+#pragma unroll
+  for (int i = 0; i < QPW; ++i) {
+    const int r = warp * QPW + i, a = a0 + r;
+    inv_sum[i] = 0.f;
+    if (a >= len) continue;   // warp-uniform
+    float m = -INFINITY;
+    for (int j = lane; j < L; j += 32) {
+      const long long f = (long long)(a + 1) * L + j;
+      const int i2 = (int)(f / (L + 1)), jj = (int)(f % (L + 1));
+      float sc = S[r * Tpad + j];
+      if (jj != 0) sc += Mx[(i2 - a0) * Tpad + jj - 1];
+      sc *= inv_sqrt;
+      S[r * Tpad + j] = sc;
+      m = fmaxf(m, sc);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) { const float e = expf(S[r * Tpad + j] - m); S[r * Tpad + j] = e; sum += e; }
+    inv_sum[i] = 1.f / warp_sum(sum);
+  }
+  constexpr int DPL = D / 32;
+  float acc[QPW][DPL];
+#pragma unroll
+  for (int i = 0; i < QPW; ++i)
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) acc[i][c] = 0.f;
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    __syncthreads();
+    load_tile(vbase, ld, j0);
+    __syncthreads();
+    const int nk = min(32, L - j0);
+    for (int jj = 0; jj < nk; ++jj) {
+      float vv[DPL];
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) vv[c] = KT[jj * KS + lane + 32 * c];
+#pragma unroll
+      for (int i = 0; i < QPW; ++i) {
+        const float p = S[(warp * QPW + i) * Tpad + j0 + jj];
+#pragma unroll
+        for (int c = 0; c < DPL; ++c) acc[i][c] += p * vv[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < QPW; ++i) {
+    const int a = a0 + warp * QPW + i;
+    if (a >= T) continue;
+#pragma unroll
+    for (int c = 0; c < DPL; ++c)
+      stany(out, ((long long)b * T + a) * out_ld + h * D + lane + 32 * c, a < len ? acc[i][c] * inv_sum[i] : 0.f, odt);
+  }
+}
+
 }  // namespace asb
 
 using namespace asb;
@@ -285,6 +428,21 @@ extern "C" int as_conformer_attention(const float* q, const float* k, const floa
   ASB_REQUIRE(D == 64, AS_ERR_SHAPE, "as_conformer_attention: head dim %d unsupported (64 only)", D);
   ASB_REQUIRE((qkv_ld % 4) == 0 && ((H * D) % 4) == 0, AS_ERR_ALIGN, "as_conformer_attention: ld must be a multiple of 4");
   const int Tpad = (T + 31) & ~31;
+  {
+    const size_t smem_t = sizeof(float) * ((size_t)(2 * CT_QT + 1) * D + 32 * (D + 4) + (size_t)(2 * CT_QT + 1) * Tpad);
+    if (smem_t <= 200 * 1024) {
+      static bool attr_t = false;
+      if (!attr_t) {
+        ASB_CUDA(cudaFuncSetAttribute(conformer_attention_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_t = true;
+      }
+      dim3 grid((T + CT_QT - 1) / CT_QT, H, B);
+      conformer_attention_tiled_kernel<64><<<grid, CT_WARPS * 32, smem_t, reinterpret_cast<cudaStream_t>(stream)>>>(
+          q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld);
+      ASB_CUDA(cudaGetLastError());
+      return AS_OK;
+    }
+  }
   const size_t smem = sizeof(float) * (size_t)CA_WARPS * (3 * D + Tpad);
   ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_conformer_attention: T=%d too long", T);
   static bool attr = false;

@@ -467,7 +467,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elected lane of a converged warp: back-to-back UTCHMMA issue (no per-instruction election loop)
       // ===== MMA issuer =====
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -600,7 +600,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elected lane of a converged warp: back-to-back UTCHMMA issue (no per-instruction election loop)
       // ===== MMA issuer =====
       mbar_wait(w_bar, 0);
       int lt = 0;
@@ -731,7 +731,7 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elected lane of a converged warp: back-to-back UTCHMMA issue (no per-instruction election loop)
       mbar_wait(w_bar, 0);
       int lt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {

@@ -7,6 +7,20 @@
 
 namespace asb {
 
+// Grid-stride loop over `total` elements with 32-bit index arithmetic whenever the count allows it:
+// 64-bit div/mod is emulated (~100 instructions) and dominated these kernels (ncu: conv_small 530 us).
+#define ASB_GRID_STRIDE(i, total, ...)                                                              \
+  if ((total) <= 0x7fffffffLL) {                                                                    \
+    const unsigned _n = (unsigned)(total);                                                          \
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < _n; i += gridDim.x * blockDim.x)   \
+      __VA_ARGS__                                                                                   \
+  } else {                                                                                          \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (total);               \
+         i += (long long)gridDim.x * blockDim.x)                                                    \
+      __VA_ARGS__                                                                                   \
+  }
+
+
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
@@ -130,10 +144,9 @@ __global__ void adain_apply_kernel(const void* __restrict__ x, int xdt, long lon
                                    long long out_ld) {
   const int To = up_w ? 2 * T : T;
   const long long total = (long long)B * To * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
-    const long long r = i / C;
+    const auto r = i / C;
     const int to = r % To;
     const int b = r / To;
     const int len = lens ? min(lens[b], T) : T;
@@ -155,6 +168,71 @@ __global__ void adain_apply_kernel(const void* __restrict__ x, int xdt, long lon
       else y = a_at(m) * up_w[c * 3 + 2] + a_at(m + 1) * up_w[c * 3 + 0] + up_b[c];
     }
     stany(out, ((long long)b * To + to) * out_ld + c, y, odt);
+  })
+}
+
+// Vector form of the kernel above (4 channels per lane, per-channel constants in registers, a warp
+// reads / writes one contiguous row segment): the norm + affine + LeakyReLU pass is pure HBM streaming.
+// grid = (C / 128, row chunks, B); requires C % 4 == 0 and 16- / 8-byte aligned rows.
+constexpr int AD_ROWS = 32;   // input rows per CTA (8 warps x 4 rows)
+
+__device__ __forceinline__ float4 ld4any(const void* p, long long off, int dt) {
+  if (dt == AS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off));
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + off));
+  return make_float4(from16(uint16_t(u.x & 0xFFFF), dt), from16(uint16_t(u.x >> 16), dt),
+                     from16(uint16_t(u.y & 0xFFFF), dt), from16(uint16_t(u.y >> 16), dt));
+}
+__device__ __forceinline__ void st4any(void* p, long long off, float4 v, int dt) {
+  if (dt == AS_F32) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + off) = v; return; }
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + off) = make_uint2(pack16(v.x, v.y, dt), pack16(v.z, v.w, dt));
+}
+
+template <bool UP>
+__global__ void __launch_bounds__(256)
+adain_apply_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, int C,
+                       const float* __restrict__ stats, const float* __restrict__ gb, long long gb_ld,
+                       float slope, const int* __restrict__ lens, const float* __restrict__ up_w,
+                       const float* __restrict__ up_b, void* out, int odt, long long out_ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  if (c >= C) return;
+  const int len = lens ? min(lens[b], T) : T;
+  float sc[4], mu[4], sh[4], w0[4], w1[4], w2[4], ub[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float mean = stats[((long long)b * C + c + e) * 2], rstd = stats[((long long)b * C + c + e) * 2 + 1];
+    const float g = 1.f + gb[(long long)b * gb_ld + c + e], be = gb[(long long)b * gb_ld + C + c + e];
+    sc[e] = rstd * g;
+    mu[e] = mean;           // subtract the mean first: bias-dominated channels (|mean| >> std) would cancel badly otherwise
+    sh[e] = be;
+    if (UP) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
+  }
+  auto act_row = [&](int t) -> float4 {
+    if (t >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = ld4any(x, ((long long)b * T + t) * x_ld + c, xdt);
+    v.x = (v.x - mu[0]) * sc[0] + sh[0]; v.y = (v.y - mu[1]) * sc[1] + sh[1];
+    v.z = (v.z - mu[2]) * sc[2] + sh[2]; v.w = (v.w - mu[3]) * sc[3] + sh[3];
+    v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+    v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+    return v;
+  };
+  const int t_end = min(T, (int)(blockIdx.y + 1) * AD_ROWS);
+  for (int t = blockIdx.y * AD_ROWS + warp; t < t_end; t += 8) {
+    const float4 a0 = act_row(t);
+    if (!UP) {
+      st4any(out, ((long long)b * T + t) * out_ld + c, a0, odt);
+    } else {
+      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
+      if (t < len) {
+        const float4 a1 = act_row(t + 1);
+        ev = make_float4(a0.x * w1[0] + ub[0], a0.y * w1[1] + ub[1], a0.z * w1[2] + ub[2], a0.w * w1[3] + ub[3]);
+        od = make_float4(a0.x * w2[0] + a1.x * w0[0] + ub[0], a0.y * w2[1] + a1.y * w0[1] + ub[1],
+                         a0.z * w2[2] + a1.z * w0[2] + ub[2], a0.w * w2[3] + a1.w * w0[3] + ub[3]);
+      }
+      st4any(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
+      st4any(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+    }
   }
 }
 
@@ -166,40 +244,49 @@ __global__ void repeat_rows_kernel(const void* __restrict__ x, int xdt, long lon
                                    long long out_ld) {
   const int To = T * rep;
   const long long total = (long long)B * To * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
-    const long long r = i / C;
+    const auto r = i / C;
     const int to = r % To;
     const int b = r / To;
     const int t = to / rep;
     const int len = lens ? min(lens[b], T) : T;
     float v = t < len ? ldany(x, ((long long)b * T + t) * x_ld + c, xdt) : 0.f;
     stany(out, ((long long)b * To + to) * out_ld + c, v, odt);
-  }
+  })
 }
 
 // ---------------------------------------------------------------------------------------------
 // length regulation: one block per item builds frame->token map by a prefix sum, then gathers
 // ---------------------------------------------------------------------------------------------
+constexpr int LR_ROWS = 32;   // output rows per CTA
+
 __global__ void length_regulate_kernel(const void* __restrict__ x, int xdt, long long x_ld, int Tt,
                                        int C, const int* __restrict__ dur,
                                        const int* __restrict__ lens_t, int rep, int To, void* out,
-                                       int odt, long long out_ld, int* __restrict__ out_lens) {
+                                       int odt, long long out_ld, int* __restrict__ out_lens, int vec) {
   extern __shared__ int cum[];  // [Tt + 1] inclusive prefix sums, cum[0] = 0
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int nt = lens_t ? min(lens_t[b], Tt) : Tt;
-  if (threadIdx.x == 0) {
-    int s = 0;
-    cum[0] = 0;
-    for (int j = 0; j < nt; ++j) { s += max(dur[(long long)b * Tt + j], 0); cum[j + 1] = s; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (warp == 0) {
+    // chunked warp scan of the durations (every CTA of the item recomputes it: Tt is a few hundred)
+    int carry = 0;
+    if (lane == 0) cum[0] = 0;
+    for (int j0 = 0; j0 < nt; j0 += 32) {
+      const int j = j0 + lane;
+      int v = j < nt ? max(dur[(long long)b * Tt + j], 0) : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      if (j < nt) cum[j + 1] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
   }
   __syncthreads();
   const int L = cum[nt];
-  if (threadIdx.x == 0 && out_lens) out_lens[b] = min(L * rep, To);
-  // each warp walks output rows; binary search of the token for the row
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = warp; r < To; r += nw) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_lens) out_lens[b] = min(L * rep, To);
+  const int r_end = min(To, (int)(blockIdx.x + 1) * LR_ROWS);
+  for (int r = blockIdx.x * LR_ROWS + warp; r < r_end; r += nw) {
     const int fr = r / rep;
     int tok = -1;
     if (fr < L) {
@@ -207,9 +294,28 @@ __global__ void length_regulate_kernel(const void* __restrict__ x, int xdt, long
       while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cum[mid] <= fr) lo = mid; else hi = mid; }
       tok = lo;
     }
-    for (int c = lane; c < C; c += 32) {
-      float v = tok >= 0 ? ldany(x, ((long long)b * Tt + tok) * x_ld + c, xdt) : 0.f;
-      stany(out, ((long long)b * To + r) * out_ld + c, v, odt);
+    const long long xo = ((long long)b * Tt + max(tok, 0)) * x_ld, yo = ((long long)b * To + r) * out_ld;
+    if (vec == 1) {          // same element size on both sides, 16-byte aligned rows: straight 16-byte copies
+      const int n16 = C * (xdt == AS_F32 ? 4 : 2) / 16;
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(x) + xo * (xdt == AS_F32 ? 4 : 2));
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + yo * (odt == AS_F32 ? 4 : 2));
+      for (int c = lane; c < n16; c += 32) dst[c] = tok >= 0 ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+    } else if (vec == 2) {   // fp32 -> 16-bit, 8 channels per lane
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + xo);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + yo);
+      for (int c = lane; c < C / 8; c += 32) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (tok >= 0) {
+          const float4 p = __ldg(src + 2 * c), q = __ldg(src + 2 * c + 1);
+          o = make_uint4(pack16(p.x, p.y, odt), pack16(p.z, p.w, odt), pack16(q.x, q.y, odt), pack16(q.z, q.w, odt));
+        }
+        dst[c] = o;
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        float v = tok >= 0 ? ldany(x, xo + c, xdt) : 0.f;
+        stany(out, yo + c, v, odt);
+      }
     }
   }
 }
@@ -227,13 +333,12 @@ __global__ void conv_small_kernel(const void* __restrict__ x, int xdt, long long
                                   long long yr_ld, void* ya, int yadt, long long ya_ld, int act,
                                   float slope) {
   const long long total = (long long)B * T * F * Cout;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int co = i % Cout;
-    const long long row = i / Cout;
+    const auto row = i / Cout;
     const int f = row % F;
     const int t = (row / F) % T;
-    const int b = row / ((long long)F * T);
+    const int b = (row / F) / T;
     float acc = bias ? bias[co] : 0.f;
     for (int j = 0; j < ntaps; ++j) {
       const int ti = t + taps.dt[j], fi = f + taps.df[j];
@@ -245,6 +350,73 @@ __global__ void conv_small_kernel(const void* __restrict__ x, int xdt, long long
     if (lens && t >= lens[b]) acc = 0.f;
     if (yr) stany(yr, row * yr_ld + co, acc, yrdt);
     if (ya) stany(ya, row * ya_ld + co, apply_act(acc, act, slope), yadt);
+  })
+}
+
+// 8 output channels per thread, weights transposed to [tap][ci][co] in shared memory, 32-bit index
+// arithmetic (the scalar kernel above spends its time in 64-bit div/mod: 530 us for the 1 -> 64
+// channel 3x3 stems of JDCNet / Mel_block on a 16 x 240 x 80 image).
+__global__ void __launch_bounds__(256)
+conv_small_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T, int F, int Cin,
+                      const float* __restrict__ w, const float* __restrict__ bias, int ntaps, SmallTaps taps,
+                      int Cout, const int* __restrict__ lens, void* yr, int yrdt, long long yr_ld, void* ya,
+                      int yadt, long long ya_ld, int act, float slope, int vec_raw, int vec_act) {
+  extern __shared__ float ws[];   // [ntaps][Cin][Cout] + bias[Cout]
+  const int nw = ntaps * Cin * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+    const int co = i % Cout, ci = (i / Cout) % Cin, j = i / (Cout * Cin);
+    ws[i] = w[((long long)j * Cout + co) * Cin + ci];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[nw + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int groups = Cout >> 3;
+  const unsigned rows = (unsigned)B * T * F;            // host guarantees rows * groups < 2^31
+  const unsigned total = rows * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned g = i % groups, row = i / groups;
+    const int f = row % F;
+    const unsigned bt = row / F;
+    const int t = bt % T, b = bt / T;
+    const int co = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = ws[nw + co + e];
+    for (int j = 0; j < ntaps; ++j) {
+      const int ti = t + taps.dt[j], fi = f + taps.df[j];
+      if (ti < 0 || ti >= T || fi < 0 || fi >= F) continue;
+      const long long xr = (((long long)b * T + ti) * F + fi) * x_ld;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float xv = ldany(x, xr + ci, xdt);
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (j * Cin + ci) * Cout + co);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (j * Cin + ci) * Cout + co + 4);
+        acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+        acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+      }
+    }
+    if (lens && t >= lens[b]) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    }
+    auto put = [&](void* y, int dt, long long ld, int vec, const float (&v)[8]) {
+      const long long o = (long long)row * ld + co;
+      if (vec && dt != AS_F32) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + o) =
+            make_uint4(pack16(v[0], v[1], dt), pack16(v[2], v[3], dt), pack16(v[4], v[5], dt), pack16(v[6], v[7], dt));
+      } else if (vec) {
+        float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o);
+        q[0] = make_float4(v[0], v[1], v[2], v[3]); q[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) stany(y, o + e, v[e], dt);
+      }
+    };
+    if (yr) put(yr, yrdt, yr_ld, vec_raw, acc);
+    if (ya) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = apply_act(acc[e], act, slope);
+      put(ya, yadt, ya_ld, vec_act, v);
+    }
   }
 }
 
@@ -258,13 +430,12 @@ __global__ void dwconv_kernel(const void* __restrict__ x, int xdt, long long x_l
                               const int* __restrict__ lens_out, int act, float slope, void* out,
                               int odt, long long out_ld) {
   const long long total = (long long)B * To * Fo * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
-    const long long row = i / C;
+    const auto row = i / C;
     const int fo = row % Fo;
     const int to = (row / Fo) % To;
-    const int b = row / ((long long)Fo * To);
+    const int b = (row / Fo) / To;
     const int len_in = lens_in ? min(lens_in[b], T) : T;
     float acc = bias ? bias[c] : 0.f;
     for (int jt = 0; jt < kt; ++jt) {
@@ -282,7 +453,7 @@ __global__ void dwconv_kernel(const void* __restrict__ x, int xdt, long long x_l
     float y = apply_act(acc, act, slope);
     if (lens_out && to >= lens_out[b]) y = 0.f;
     stany(out, row * out_ld + c, y, odt);
-  }
+  })
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,13 +464,12 @@ __global__ void avgpool_kernel(const void* __restrict__ x, int xdt, long long x_
                                long long out_ld) {
   const long long total = (long long)B * To * Fo * C;
   const float inv = 1.f / (pt * pf);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
-    const long long row = i / C;
+    const auto row = i / C;
     const int fo = row % Fo;
     const int to = (row / Fo) % To;
-    const int b = row / ((long long)Fo * To);
+    const int b = (row / Fo) / To;
     float acc = 0.f;
     for (int jt = 0; jt < pt; ++jt) {
       const int ti = min(to * pt + jt, T - 1);  // replicate the last column when T is odd
@@ -309,7 +479,7 @@ __global__ void avgpool_kernel(const void* __restrict__ x, int xdt, long long x_
       }
     }
     stany(out, row * out_ld + c, acc * inv, odt);
-  }
+  })
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -320,12 +490,11 @@ __global__ void affine_act_maxpool_kernel(const void* __restrict__ x, int xdt, l
                                           const float* __restrict__ shift, float slope, int pf, int Fo,
                                           void* out, int odt, long long out_ld) {
   const long long total = (long long)B * T * Fo * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
-    const long long row = i / C;
+    const auto row = i / C;
     const int fo = row % Fo;
-    const long long bt = row / Fo;
+    const auto bt = row / Fo;
     const float sc = scale[c], sh = shift[c];
     float m = -INFINITY;
     for (int j = 0; j < pf; ++j) {
@@ -334,7 +503,7 @@ __global__ void affine_act_maxpool_kernel(const void* __restrict__ x, int xdt, l
       m = fmaxf(m, v);
     }
     stany(out, row * out_ld + c, m, odt);
-  }
+  })
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -365,16 +534,15 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 __global__ void lstm_onestep_kernel(const float* __restrict__ xp, long long xp_ld, long long rows, int H,
                                     void* out, int odt, long long out_ld) {
   const long long total = rows * 2 * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  ASB_GRID_STRIDE(i, total, {
     const int j = i % H;
     const int dir = (i / H) % 2;
-    const long long row = i / (2 * H);
+    const auto row = i / (2 * H);
     const float* g = xp + row * xp_ld + (long long)dir * 4 * H;
     const float ig = sigmoidf_(g[j]), gg = tanhf(g[2 * H + j]), og = sigmoidf_(g[3 * H + j]);
     const float c = ig * gg;
     stany(out, row * out_ld + dir * H + j, og * tanhf(c), odt);
-  }
+  })
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,6 +669,21 @@ extern "C" int as_adain_apply(const void* x, int32_t x_dtype, int64_t x_ld, int3
   if (total == 0) return AS_OK;
   ASB_REQUIRE(x && stats && gb && out, AS_ERR_SHAPE, "as_adain_apply: null pointer");
   ASB_REQUIRE(!up_w || up_b, AS_ERR_SHAPE, "as_adain_apply: up_w without up_b");
+  {
+    auto row_ok = [](const void* ptr, long long ld, int dt) {
+      const int es = dt == AS_F32 ? 4 : 2;
+      return (reinterpret_cast<uintptr_t>(ptr) % (4 * es)) == 0 && ((ld * es) % (4 * es)) == 0;
+    };
+    if ((C % 4) == 0 && row_ok(x, x_ld, x_dtype) && row_ok(out, out_ld, out_dtype)) {
+      dim3 grid((unsigned)cdiv(C, 128), (unsigned)cdiv(T, AD_ROWS), (unsigned)B);
+      if (up_w) adain_apply_vec_kernel<true><<<grid, 256, 0, ST(stream)>>>(x, x_dtype, x_ld, T, C, stats, gb, gb_ld, slope, lens,
+                                                                           up_w, up_b, out, out_dtype, out_ld);
+      else adain_apply_vec_kernel<false><<<grid, 256, 0, ST(stream)>>>(x, x_dtype, x_ld, T, C, stats, gb, gb_ld, slope, lens,
+                                                                       up_w, up_b, out, out_dtype, out_ld);
+      ASB_CUDA(cudaGetLastError());
+      return AS_OK;
+    }
+  }
   adain_apply_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, C, stats, gb, gb_ld, slope,
                                                             lens, up_w, up_b, out, out_dtype, out_ld);
   ASB_CUDA(cudaGetLastError());
@@ -526,8 +709,17 @@ extern "C" int as_length_regulate(const void* x, int32_t x_dtype, int64_t x_ld, 
   ASB_REQUIRE(x && dur && out && rep >= 1 && Tt > 0 && To >= 0, AS_ERR_SHAPE, "as_length_regulate: bad argument");
   const size_t smem = (size_t)(Tt + 1) * sizeof(int);
   ASB_REQUIRE(smem <= 48 * 1024, AS_ERR_SHAPE, "as_length_regulate: Tt=%d too large", Tt);
-  length_regulate_kernel<<<B, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, Tt, C, dur, lens_t, rep, To, out,
-                                                      out_dtype, out_ld, out_lens);
+  auto al16 = [](const void* ptr, long long ld, int dt) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld * (dt == AS_F32 ? 4 : 2)) & 15) == 0;
+  };
+  int vec = 0;
+  if (al16(x, x_ld, x_dtype) && al16(out, out_ld, out_dtype)) {
+    if (x_dtype == out_dtype && (C * (x_dtype == AS_F32 ? 4 : 2)) % 16 == 0) vec = 1;
+    else if (x_dtype == AS_F32 && out_dtype != AS_F32 && C % 8 == 0) vec = 2;
+  }
+  dim3 grid((unsigned)((To + LR_ROWS - 1) / LR_ROWS > 0 ? (To + LR_ROWS - 1) / LR_ROWS : 1), (unsigned)B);
+  length_regulate_kernel<<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, Tt, C, dur, lens_t, rep, To, out,
+                                                         out_dtype, out_ld, out_lens, vec);
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -545,6 +737,17 @@ extern "C" int as_conv_small(const void* x, int32_t x_dtype, int64_t x_ld, int32
               "as_conv_small: ntaps=%d Cin=%d unsupported", ntaps, Cin);
   SmallTaps taps;
   for (int j = 0; j < CS_MAX_TAPS; ++j) { taps.dt[j] = j < ntaps ? tap_dt[j] : 0; taps.df[j] = j < ntaps ? tap_df[j] : 0; }
+  const size_t wsmem = ((size_t)ntaps * Cin * Cout + Cout) * sizeof(float);
+  if ((Cout % 8) == 0 && wsmem <= 40 * 1024 && total < (1ll << 31)) {
+    auto al16 = [](const void* ptr, long long ld, int dt) {
+      return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld * (dt == AS_F32 ? 4 : 2)) & 15) == 0;
+    };
+    conv_small_vec_kernel<<<ew_grid(total / 8), 256, wsmem, ST(stream)>>>(
+        x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps, Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
+        y_act_dtype, y_act_ld, act, slope, al16(y_raw, y_raw_ld, y_raw_dtype) ? 1 : 0, al16(y_act, y_act_ld, y_act_dtype) ? 1 : 0);
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
   conv_small_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps,
                                                            Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
                                                            y_act_dtype, y_act_ld, act, slope);

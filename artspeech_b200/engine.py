@@ -22,8 +22,19 @@ HOP = 300
 
 
 class Synthesizer:
-    def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True):
+    """``pipeline_depth`` > 1 keeps that many calls in flight: call ``i`` runs on side stream ``i % depth``
+    with its own CUDA-graph instance and buffers, so the latency-bound acoustic model of one batch
+    overlaps the throughput-bound vocoder of the previous one.  The outputs of a pipelined call are
+    produced on ``last_stream``: consume them there (``with torch.cuda.stream(syn.last_stream)``) or
+    after ``join()``, which makes the current stream wait for every call issued so far."""
+
+    def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True, pipeline_depth: int = 1):
         self.device = torch.device(device)
+        self.pipeline_depth = max(1, int(pipeline_depth))
+        self._slot_streams = None
+        self._slot_done = {}
+        self._calls = 0
+        self.last_stream = None
         self.model = model.to(self.device).eval()
         self.model.distribution = {k: v.to(self.device) for k, v in self.model.distribution.items()}
         self.generator = generator.to(self.device).eval()
@@ -44,6 +55,7 @@ class Synthesizer:
         pass sync-free), ``mels`` fp32 [B,80,Tr] (device), ``durations`` int64 [B,Tt] (HOST) or None
         (use the duration predictor; costs one device->host sync).
         Returns (wav fp32 [B, 300*Tm_max], mel_lengths int32 [B] (device), mel fp32 [B,80,Tm_max])."""
+        self.last_stream = torch.cuda.current_stream(self.device)
         host_side = durations is not None and not durations.is_cuda and not tok_lens.is_cuda and not mel_lens.is_cuda
         if not host_side:
             return self._forward(tokens, tok_lens, mels, mel_lens, durations)
@@ -54,7 +66,16 @@ class Synthesizer:
         if not graphable:
             return self._forward(tokens, tok_lens.to(self.device), mels, mel_lens.to(self.device),
                                  durations.to(self.device), meta)
-        key = (tuple(tokens.shape), tuple(mels.shape), tuple(tl), tuple(ml), hash(durations.numpy().tobytes()))
+        slot = 0
+        cur = torch.cuda.current_stream(self.device)
+        run_stream = cur
+        if self.pipeline_depth > 1:
+            if self._slot_streams is None:
+                self._slot_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.pipeline_depth)]
+            slot = self._calls % self.pipeline_depth
+            run_stream = self._slot_streams[slot]
+        self._calls += 1
+        key = (slot, tuple(tokens.shape), tuple(mels.shape), tuple(tl), tuple(ml), hash(durations.numpy().tobytes()))
         entry = self._graphs.get(key)
         if entry is None:
             static_tok = tokens.clone()
@@ -63,25 +84,46 @@ class Synthesizer:
             durations = durations.to(self.device)
             # warm-up on a side stream (weight packing, cudaFuncSetAttribute, allocator)
             s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
+            s.wait_stream(cur)
             with torch.cuda.stream(s):
                 for _ in range(2):
                     self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta)
-            torch.cuda.current_stream(self.device).wait_stream(s)
+            cur.wait_stream(s)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             before = ops.launch_count
             with torch.cuda.graph(g):
                 out = self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta)
             self.launches_per_call = ops.launch_count - before
-            entry = (g, static_tok, static_mel, out)
+            # the captured kernels read these device tensors on every replay: keep them alive with the graph
+            entry = (g, static_tok, static_mel, out, (tok_lens, mel_lens, durations))
             self._graphs[key] = entry
-        g, static_tok, static_mel, out = entry
-        static_tok.copy_(tokens, non_blocking=True)
-        static_mel.copy_(mels, non_blocking=True)
-        g.replay()
+        g, static_tok, static_mel, out, _keepalive = entry
+        if run_stream is not cur:
+            # the slot's stream picks up after whatever produced the inputs on the caller's stream;
+            # the caller's stream never waits for the slot (that would serialise the pipeline)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            run_stream.wait_event(ready)
+            tokens.record_stream(run_stream)
+            mels.record_stream(run_stream)
+        with torch.cuda.stream(run_stream):
+            static_tok.copy_(tokens, non_blocking=True)
+            static_mel.copy_(mels, non_blocking=True)
+            g.replay()
+            if run_stream is not cur:
+                done = torch.cuda.Event()
+                done.record(run_stream)
+                self._slot_done[slot] = done
+        self.last_stream = run_stream
         ops._count(self.launches_per_call)
         return out
+
+    def join(self):
+        """Make the current stream wait for every pipelined call issued so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._slot_done.values():
+            cur.wait_event(ev)
 
 
 # -------------------------------------------------------------------------------------------

@@ -181,13 +181,16 @@ def run_ours(args):
 
     model = checkpoint.build_random_artsspeech(0)
     gen = checkpoint.build_random_generator(0)
-    syn = engine.Synthesizer(model, gen, device=dev, use_cuda_graph=not args.no_graph)
+    syn = engine.Synthesizer(model, gen, device=dev, use_cuda_graph=not args.no_graph,
+                             pipeline_depth=1 if args.no_graph else args.pipeline)
 
     tokens, tok_lens, mels, mel_lens, dur = make_inputs(rank)
     tok_d, mel_d = tokens.to(dev), mels.to(dev)
     # pinned host staging for the end-to-end arm
     tok_h, mel_h = tokens.pin_memory(), mels.pin_memory()
-    wav_h = torch.empty(B_PER_GPU, FRAMES * 300, dtype=torch.float32).pin_memory()
+    wav_hs = [torch.empty(B_PER_GPU, FRAMES * 300, dtype=torch.float32).pin_memory() for _ in range(max(args.pipeline, 1))]
+    wav_h = wav_hs[0]
+    calls = [0]
 
     def step_resident():
         return syn.synthesize(tok_d, tok_lens, mel_d, mel_lens, dur)
@@ -196,9 +199,12 @@ def run_ours(args):
         t = tok_h.to(dev, non_blocking=True)
         m = mel_h.to(dev, non_blocking=True)
         wav, _, _ = syn.synthesize(t, tok_lens, m, mel_lens, dur)
-        if world > 1:
-            gathered, _ = engine.gather_waveforms(wav, torch.full((wav.shape[0],), wav.shape[1], device=dev))
-        wav_h.copy_(wav, non_blocking=True)
+        calls[0] += 1
+        # the waveforms are produced on the engine's stream for this call: gather / D2H follow on that stream
+        with torch.cuda.stream(syn.last_stream):
+            if world > 1:
+                gathered, _ = engine.gather_waveforms(wav, torch.full((wav.shape[0],), wav.shape[1], device=dev))
+            wav_hs[calls[0] % len(wav_hs)].copy_(wav, non_blocking=True)
         return wav
 
     def barrier():
@@ -212,6 +218,7 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        syn.join()                 # pipelined calls run on the engine's streams: the end event waits for all of them
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -240,6 +247,7 @@ def run_ours(args):
     # dominant kernel family: the vocoder's implicit-GEMM convolutions (78 conv launches, nothing else).
     # Timed alone, replayed from a CUDA graph (no launch gaps), with CUDA events on the launch stream.
     _, lens_m, mel_out = step_resident()
+    syn.join()
     mel_static = mel_out.clone()
     lens_static = lens_m.clone()
     side = torch.cuda.Stream(device=dev)
@@ -309,7 +317,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "utterances_per_gpu": B_PER_GPU, "tokens": TT, "ref_frames": TR,
                    "mel_frames": FRAMES, "audio_s_per_step_per_gpu": B_PER_GPU * AUDIO_S_PER_UTT,
                    "weights": "random-init conditioned (seed 0); vocoder checkpoint g_00935000 not available",
-                   "cuda_graph": not args.no_graph,
+                   "cuda_graph": not args.no_graph, "batches_in_flight": 1 if args.no_graph else args.pipeline,
                    "l2": "activations streamed per step >> 126 MB L2, no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(tok_h.numel() * 8 + mel_h.numel() * 4),
@@ -343,6 +351,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="batches in flight per GPU (2: the acoustic model of step i+1 overlaps the vocoder of step i)")
     ap.add_argument("--cpu-utts", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -135,10 +135,7 @@ class StyleEncoder(nn_util.PlanMixin, nn.Module):
         feat = torch.zeros(B, T, 88, dtype=dt, device=dev)                   # F0 | energy | mel (| pad)
         ops.to_channels_last(mel, dt, out=feat[..., 2:82])
         mel_cl = ops.to_channels_last(mel, dt)                               # [B,T,80]
-        f0_raw = self.pitch_extractor.forward_cl(mel_cl.view(B, T, M, 1))    # [B,T,1] (:432)
-        ops.to_channels_last(f0_raw.view(B, 1, T), dt, out=feat[..., 0:1])
         ops.to_channels_last(n_raw.view(B, 1, T), dt, out=feat[..., 1:2])
-        ema_raw = self.ema_extractor.forward_cl(feat[..., :82])              # [B,T,10] (:433)
 
         # z-normalisation with the dataset statistics (:447-449)
         def znorm(x_cl, mean, std):
@@ -147,17 +144,38 @@ class StyleEncoder(nn_util.PlanMixin, nn.Module):
             mul = (1.0 / std.to(dev).float().reshape(-1)).expand(C).contiguous()
             cf = ops.to_channels_first(x_cl, torch.float32, sub=sub, mul=mul)           # [B,C,T]
             return cf, ops.to_channels_last(cf, torch.float32)
-        n_cf, n_cl = znorm(n_raw.view(B, T, 1), distribution["energy_mean"], distribution["energy_std"])
-        f0_cf, f0_cl = znorm(f0_raw, distribution["pitch_mean"], distribution["pitch_std"])
-        ema_cf, ema_cl = znorm(ema_raw, distribution["EMA_mean"], distribution["EMA_std"])
 
         # crop to the first T-1 frames (:459-466 with equal lengths => random_start == 0)
         Tc = T - 1
         crop = lambda x_cl: x_cl[:, :Tc].contiguous()
-        mel_img = crop(mel_cl).view(B, Tc, M, 1)
-        ema_img = crop(ema_cl).view(B, Tc, 10, 1)
-        pooled = [_run_stack_2d(p["mel"], mel_img, dt), _run_stack_2d(p["ema"], ema_img, dt),
-                  _run_stack_1d(p["f0"], crop(f0_cl), dt), _run_stack_1d(p["en"], crop(n_cl), dt)]
+
+        # Dependencies (:431-433, :447-466): the mel style stack needs only the mel, the energy stack only
+        # log_norm; F0 comes from JDCNet, EMA from the conformer predictor fed with (F0, energy, mel).
+        # The chain JDCNet -> EMA predictor -> EMA stack is the long one; everything else runs beside it.
+        def mel_branch():
+            return _run_stack_2d(p["mel"], crop(mel_cl).view(B, Tc, M, 1), dt)
+
+        def energy_branch():
+            n_cf, n_cl = znorm(n_raw.view(B, T, 1), distribution["energy_mean"], distribution["energy_std"])
+            return n_cf, n_cl, _run_stack_1d(p["en"], crop(n_cl), dt)
+
+        def pitch_chain():
+            f0_raw = self.pitch_extractor.forward_cl(mel_cl.view(B, T, M, 1))    # [B,T,1] (:432)
+            ops.to_channels_last(f0_raw.view(B, 1, T), dt, out=feat[..., 0:1])
+
+            def f0_branch():
+                f0_cf, f0_cl = znorm(f0_raw, distribution["pitch_mean"], distribution["pitch_std"])
+                return f0_cf, f0_cl, _run_stack_1d(p["f0"], crop(f0_cl), dt)
+
+            def ema_branch():
+                ema_raw = self.ema_extractor.forward_cl(feat[..., :82])          # [B,T,10] (:433)
+                ema_cf, ema_cl = znorm(ema_raw, distribution["EMA_mean"], distribution["EMA_std"])
+                return ema_cf, ema_cl, _run_stack_2d(p["ema"], crop(ema_cl).view(B, Tc, 10, 1), dt)
+            return ops.run_concurrently([f0_branch, ema_branch], dev, pool="style.pitch")
+
+        pooled_mel, (n_cf, n_cl, pooled_en), ((f0_cf, f0_cl, pooled_f0), (ema_cf, ema_cl, pooled_ema)) = \
+            ops.run_concurrently([mel_branch, energy_branch, pitch_chain], dev, pool="style")
+        pooled = [pooled_mel, pooled_ema, pooled_f0, pooled_en]
         style = torch.empty(1, B, 2 * self.style_dim, dtype=torch.float32, device=dev)
         off = 0
         for pl, head in zip(pooled, p["heads"]):

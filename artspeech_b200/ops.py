@@ -508,7 +508,7 @@ def to_channels_first(src, out_dtype, lens=None, sub=None, mul=None):
 _side_streams = {}
 
 
-def run_concurrently(fns, device):
+def run_concurrently(fns, device, pool: str = "main"):
     """Run the callables ``fns`` on separate CUDA streams forked from / joined to the current one
     and return their results.  Independent branches of the model (the three encoders, the three
     predictor branches) are latency-bound chains of small kernels: overlapping them fills the SMs.
@@ -517,7 +517,8 @@ def run_concurrently(fns, device):
         return [f() for f in fns]
     dev = torch.device(device)
     main = torch.cuda.current_stream(dev)
-    pool = _side_streams.setdefault((dev.index, len(fns)), [torch.cuda.Stream(device=dev) for _ in fns])
+    # nested forks name their own pool: reusing the parent's streams would serialise the branches
+    pool = _side_streams.setdefault((dev.index, pool, len(fns)), [torch.cuda.Stream(device=dev) for _ in fns])
     fork = torch.cuda.Event()
     fork.record(main)
     results, joins = [], []

@@ -244,7 +244,8 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
 
-    # dominant kernel family: the vocoder's implicit-GEMM convolutions (78 conv launches, nothing else).
+    # dominant kernel family: the vocoder's tensor-core convolutions (27 fused resblock-pair launches + 24
+    # implicit-GEMM launches, nothing else).
     # Timed alone, replayed from a CUDA graph (no launch gaps), with CUDA events on the launch stream.
     _, lens_m, mel_out = step_resident()
     syn.join()
@@ -324,7 +325,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(wav_h.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": f"conv_igemm / conv_halo_sw kernels (vocoder, {voc_launches} launches per step)",
+        "roofline": {"bound": "tensor", "kernel": f"resblock_pair + conv_igemm kernels (vocoder, {voc_launches} launches per step)",
                      "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_tflops_sustained"], "traffic": vocoder_traffic(),
                      "peak_source": pk["source"] + " sustained bf16 (kernel family timed inside a long step)",

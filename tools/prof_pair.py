@@ -1,5 +1,5 @@
 """Time as_hifigan_resblock_pair at the bench workload's stage sizes (16 utterances x 800 mel frames):
-python tools/prof_pair.py [reps]   -> per (C, k, dil): us, TFLOP/s, algorithmic GB/s"""
+python tools/prof_pair.py [reps [C [k [dil]]]]   -> per (C, k, dil): us, TFLOP/s, algorithmic GB/s"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +7,9 @@ from artspeech_b200 import ops
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-    only = [int(v) for v in sys.argv[2:]]
+    only = [int(v) for v in sys.argv[2:3]]
+    only_k = int(sys.argv[3]) if len(sys.argv) > 3 else None
+    only_d = int(sys.argv[4]) if len(sys.argv) > 4 else None
     dt = torch.bfloat16
     B = 16
     tot = 0.0
@@ -18,6 +20,8 @@ def main():
         out = torch.empty_like(xa)
         for k in (3, 7, 11):
             for dil in (1, 3, 5):
+                if (only_k is not None and k != only_k) or (only_d is not None and dil != only_d):
+                    continue
                 w1 = torch.randn(k, C, C) / (C * k) ** 0.5
                 w2 = torch.randn(k, C, C) / (C * k) ** 0.5
                 b1, b2 = torch.randn(C) * 0.1, torch.randn(C) * 0.1

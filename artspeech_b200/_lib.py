@@ -110,6 +110,7 @@ SIGNATURES.update({
     "as_conformer_attention": (C.c_int, [_V, _V, _V, _L, _V, _V, _V, _I, _I, _I, _I, _V, _V, _I, _L, _V]),
     "as_instnorm_stats": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _F, _V, _V]),
     "as_adain_apply": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _V, _L, _F, _V, _V, _V, _V, _I, _L, _V]),
+    "as_adain_norm_apply": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _L, _F, _F, _V, _V, _V, _V, _I, _L, _V, _V]),
     "as_repeat_rows": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _I, _L, _V]),
     "as_length_regulate": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _V, _I, _I, _V, _I, _L, _V, _V]),
     "as_conv_small": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _I, c_i32_p, c_i32_p, _I, _V,

@@ -104,13 +104,11 @@ def run_adain_block(p, x, gb1, gb2, lens, dt, out=None, out16=None, x16=None, re
     ``x`` when that already is 16-bit).  The result is written as ``res_dtype`` (default ``dt``) into
     ``out`` (or a new tensor) and, when ``out16`` is given (dtype or view), additionally as a 16-bit
     copy for the next block's 1x1 shortcut.  Returns (out, out16, lens'); T' = 2T for upsample."""
-    st1 = ops.instnorm_stats(x, lens)
-    a1 = ops.adain_apply(x, st1, gb1, LRELU, lens, dt, p["up_w"], p["up_b"])
+    a1 = ops.adain_norm(x, gb1, LRELU, lens, dt, p["up_w"], p["up_b"])
     up = p["up_w"] is not None
     lens2 = lens * 2 if (up and lens is not None) else lens
     c1, _ = ops.conv(a1, p["conv1"], raw=mid_dtype, lens=lens2)
-    st2 = ops.instnorm_stats(c1, lens2)
-    a2 = ops.adain_apply(c1, st2, gb2, LRELU, lens2, dt)
+    a2 = ops.adain_norm(c1, gb2, LRELU, lens2, dt)
     if p["sc"] is not None:
         xs = x16 if x16 is not None else x
         if xs.dtype != dt:

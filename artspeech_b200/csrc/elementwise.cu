@@ -236,6 +236,75 @@ adain_apply_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int 
   }
 }
 
+// InstanceNorm statistics + AdaIN + LeakyReLU (+ pool) in ONE pass over HBM: a CTA owns 32 channels of one
+// item, keeps the whole [T, 32] fp32 slab in shared memory (T <= 1536), computes the exact two-pass
+// mean / biased variance from it and writes the activated tensor.  Replaces the stats + apply launches
+// (3 reads + 1 write of the tensor -> 1 read + 1 write).
+constexpr int ADF_MAX_T = 1536;
+
+template <bool UP>
+__global__ void __launch_bounds__(256)
+adain_fused_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, int C,
+                   const float* __restrict__ gb, long long gb_ld, float eps, float slope,
+                   const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
+                   void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
+  extern __shared__ float slab[];            // [T][32]
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int b = blockIdx.y, c = blockIdx.x * 32 + lane;
+  const bool cok = c < C;
+  const int len = lens ? min(lens[b], T) : T;
+  const long long base = (long long)b * T * x_ld;
+  float s = 0.f;
+  for (int t = ty; t < len; t += 8) {
+    const float v = cok ? ldany(x, base + (long long)t * x_ld + c, xdt) : 0.f;
+    slab[t * 32 + lane] = v;
+    s += v;
+  }
+  red[ty][lane] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i][lane];
+  const float mean = len > 0 ? tot / len : 0.f;
+  __syncthreads();
+  float q = 0.f;
+  for (int t = ty; t < len; t += 8) { const float d = slab[t * 32 + lane] - mean; q += d * d; }
+  red[ty][lane] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) var += red[i][lane];
+  var = len > 0 ? var / len : 0.f;
+  const float rstd = rsqrtf(var + eps);
+  if (!cok) return;
+  if (stats_out != nullptr && ty == 0) {
+    stats_out[((long long)b * C + c) * 2] = mean;
+    stats_out[((long long)b * C + c) * 2 + 1] = rstd;
+  }
+  const float sc = rstd * (1.f + gb[(long long)b * gb_ld + c]), be = gb[(long long)b * gb_ld + C + c];
+  auto act_at = [&](int t) -> float {
+    if (t >= len) return 0.f;
+    const float v = (slab[t * 32 + lane] - mean) * sc + be;
+    return v > 0.f ? v : v * slope;
+  };
+  if (!UP) {
+    for (int t = ty; t < T; t += 8) stany(out, ((long long)b * T + t) * out_ld + c, act_at(t), odt);
+  } else {
+    const float w0 = up_w[c * 3], w1 = up_w[c * 3 + 1], w2 = up_w[c * 3 + 2], ub = up_b[c];
+    for (int t = ty; t < T; t += 8) {
+      float ev = 0.f, od = 0.f;
+      if (t < len) {
+        const float a0 = act_at(t), a1 = act_at(t + 1);
+        ev = a0 * w1 + ub;
+        od = a0 * w2 + a1 * w0 + ub;
+      }
+      stany(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
+      stany(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // nearest upsample along T
 // ---------------------------------------------------------------------------------------------
@@ -454,6 +523,53 @@ __global__ void dwconv_kernel(const void* __restrict__ x, int xdt, long long x_l
     if (lens_out && to >= lens_out[b]) y = 0.f;
     stany(out, row * out_ld + c, y, odt);
   })
+}
+
+// Time-only depthwise convolution with stride 1 (the conformer's k = 31 module, convolution.py:136-149):
+// the generic kernel recomputes the GLU of every input 31 times and reads it from global memory per
+// tap (104 us under ncu).  Here a CTA stages a (64 + k - 1) x 64-channel tile of GLU'd inputs in
+// shared memory once; each thread keeps its channel's taps in registers.
+constexpr int DWT_ROWS = 64, DWT_CH = 64, DWT_MAXK = 32;
+
+__global__ void __launch_bounds__(256)
+dwconv_time_tiled_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, int C, int glu,
+                         const float* __restrict__ w, const float* __restrict__ bias, int kt, int pt,
+                         const int* __restrict__ lens_in, const int* __restrict__ lens_out, int act,
+                         float slope, void* out, int odt, long long out_ld) {
+  extern __shared__ float tile[];   // [DWT_ROWS + kt - 1][DWT_CH]
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int b = blockIdx.z, t0 = blockIdx.y * DWT_ROWS, c = blockIdx.x * DWT_CH + tx;
+  const int len_in = lens_in ? min(lens_in[b], T) : T;
+  const int nrows = DWT_ROWS + kt - 1;
+  const bool cok = c < C;
+  for (int r = ty; r < nrows; r += 4) {
+    const int ti = t0 - pt + r;
+    float v = 0.f;
+    if (cok && ti >= 0 && ti < len_in) {
+      const long long xr = ((long long)b * T + ti) * x_ld;
+      v = ldany(x, xr + c, xdt);
+      if (glu) { const float g = ldany(x, xr + C + c, xdt); v = v / (1.f + __expf(-g)); }
+    }
+    tile[r * DWT_CH + tx] = v;
+  }
+  float wr[DWT_MAXK];
+#pragma unroll
+  for (int j = 0; j < DWT_MAXK; ++j) wr[j] = (cok && j < kt) ? w[j * C + c] : 0.f;
+  const float bv = (cok && bias) ? bias[c] : 0.f;
+  __syncthreads();
+  if (!cok) return;
+  const int len_out = lens_out ? lens_out[b] : T;
+  for (int r = ty; r < DWT_ROWS; r += 4) {
+    const int to = t0 + r;
+    if (to >= T) break;
+    float acc = bv;
+#pragma unroll
+    for (int j = 0; j < DWT_MAXK; ++j)
+      if (j < kt) acc += tile[(r + j) * DWT_CH + tx] * wr[j];
+    float y = apply_act(acc, act, slope);
+    if (to >= len_out) y = 0.f;
+    stany(out, ((long long)b * T + to) * out_ld + c, y, odt);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -690,6 +806,35 @@ extern "C" int as_adain_apply(const void* x, int32_t x_dtype, int64_t x_ld, int3
   return AS_OK;
 }
 
+extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T,
+                                   int32_t C, const float* gb, int64_t gb_ld, float eps, float slope,
+                                   const int32_t* lens, const float* up_w, const float* up_b, void* out,
+                                   int32_t out_dtype, int64_t out_ld, float* stats, void* stream) {
+  if ((long long)B * T * C == 0) return AS_OK;
+  ASB_REQUIRE(x && gb && out && stats && dt_ok(x_dtype), AS_ERR_SHAPE, "as_adain_norm_apply: bad argument");
+  ASB_REQUIRE(!up_w || up_b, AS_ERR_SHAPE, "as_adain_norm_apply: up_w without up_b");
+  if (T <= ADF_MAX_T) {
+    const size_t smem = (size_t)T * 32 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      ASB_CUDA(cudaFuncSetAttribute(adain_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADF_MAX_T * 32 * 4));
+      ASB_CUDA(cudaFuncSetAttribute(adain_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADF_MAX_T * 32 * 4));
+      attr = true;
+    }
+    dim3 grid(cdiv(C, 32), (unsigned)B);
+    if (up_w) adain_fused_kernel<true><<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, T, C, gb, gb_ld, eps, slope, lens, up_w,
+                                                                       up_b, out, out_dtype, out_ld, stats);
+    else adain_fused_kernel<false><<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, T, C, gb, gb_ld, eps, slope, lens, up_w,
+                                                                   up_b, out, out_dtype, out_ld, stats);
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
+  // long sequences: statistics pass + streaming apply pass
+  int rc = as_instnorm_stats(x, x_dtype, x_ld, B, T, C, lens, eps, stats, stream);
+  if (rc != AS_OK) return rc;
+  return as_adain_apply(x, x_dtype, x_ld, B, T, C, stats, gb, gb_ld, slope, lens, up_w, up_b, out, out_dtype, out_ld, stream);
+}
+
 extern "C" int as_repeat_rows(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T,
                               int32_t C, int32_t rep, const int32_t* lens, void* out,
                               int32_t out_dtype, int64_t out_ld, void* stream) {
@@ -763,6 +908,14 @@ extern "C" int as_dwconv(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B
   const long long total = (long long)B * To * Fo * C;
   if (total == 0) return AS_OK;
   ASB_REQUIRE(x && w && out && kt >= 1 && kf >= 1 && st >= 1 && sf >= 1, AS_ERR_SHAPE, "as_dwconv: bad argument");
+  if (F == 1 && Fo == 1 && kf == 1 && sf == 1 && st == 1 && pf == 0 && To == T && kt <= DWT_MAXK && kt >= 5) {
+    dim3 grid(cdiv(C, DWT_CH), cdiv(T, DWT_ROWS), (unsigned)B);
+    const size_t smem = (size_t)(DWT_ROWS + kt - 1) * DWT_CH * sizeof(float);
+    dwconv_time_tiled_kernel<<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, T, C, glu, w, bias, kt, pt, lens_in, lens_out,
+                                                            act, slope, out, out_dtype, out_ld);
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
   dwconv_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, F, C, glu, w, bias, kt, kf, st, sf,
                                                        pt, pf, To, Fo, lens_in, lens_out, act, slope, out,
                                                        out_dtype, out_ld);

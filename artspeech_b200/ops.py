@@ -341,6 +341,20 @@ def adain_apply(x, stats, gb, slope, lens, out_dtype, up_w=None, up_b=None, out=
     return out
 
 
+def adain_norm(x, gb, slope, lens, out_dtype, up_w=None, up_b=None, eps=1e-5):
+    """InstanceNorm statistics + AdaIN + LeakyReLU (+ pool) in one launch (``as_adain_norm_apply``)."""
+    _require_cuda(x, "adain_norm")
+    B, T, C_ = x.shape
+    To = 2 * T if up_w is not None else T
+    out = torch.empty(B, To, C_, dtype=out_dtype, device=x.device)
+    st = torch.empty(B, C_, 2, dtype=torch.float32, device=x.device)
+    assert gb.shape == (B, 2 * C_) and gb.stride(1) == 1
+    _run("as_adain_norm_apply", x, x.data_ptr(), dtype_code(x.dtype), _rows_ld(x, "adain.x"), B, T, C_,
+         gb.data_ptr(), gb.stride(0), float(eps), float(slope), _p(_i32(lens, "adain")), _p(up_w), _p(up_b),
+         out.data_ptr(), dtype_code(out.dtype), _rows_ld(out, "adain.out"), st.data_ptr())
+    return out
+
+
 def repeat_rows(x, rep, lens, out_dtype=None, out=None):
     _require_cuda(x, "repeat_rows")
     B, T, C_ = x.shape

@@ -190,6 +190,10 @@ def adain_apply(x, stats, gb, slope, lens, out_dtype, up_w=None, up_b=None, out=
     return out
 
 
+def adain_norm(x, gb, slope, lens, out_dtype, up_w=None, up_b=None, eps=1e-5):
+    return adain_apply(x, instnorm_stats(x, lens, eps), gb, slope, lens, out_dtype, up_w, up_b)
+
+
 def repeat_rows(x, rep, lens, out_dtype=None, out=None):
     y = _mask_rows(x.float(), lens, x.shape[1]).repeat_interleave(rep, dim=1)
     if out is None:
@@ -342,7 +346,7 @@ def to_channels_first(src, out_dtype, lens=None, sub=None, mul=None):
 
 
 SIM_FUNCS = ["conv", "resblock_pair", "embed", "layernorm", "relpos_attention", "conformer_attention", "instnorm_stats",
-             "adain_apply", "repeat_rows", "length_regulate", "conv_small", "dwconv", "avgpool",
+             "adain_apply", "adain_norm", "repeat_rows", "length_regulate", "conv_small", "dwconv", "avgpool",
              "affine_act_maxpool", "global_avgpool", "bilstm", "lstm_onestep", "log_norm",
              "to_channels_last", "to_channels_first"]
 

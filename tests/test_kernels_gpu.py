@@ -181,6 +181,23 @@ def test_instnorm_adain(up):
     _close(out, ref, 2e-3, "adain")
 
 
+@pytest.mark.parametrize("up", [False, True])
+@pytest.mark.parametrize("shape", [(3, 100, 96), (2, 801, 512), (1, 1600, 64)])
+def test_adain_norm_fused(shape, up):
+    """as_adain_norm_apply (single pass, slab in shared memory; T > 1536 takes the two-pass path)."""
+    B, T, C = shape
+    torch.manual_seed(3)
+    x = torch.randn(B, T, C) * 0.7 + torch.randn(C) * 30.0       # bias-dominated channels (|mean| >> std)
+    gb = torch.randn(B, 2 * C) * 0.3
+    lens = _lens(B, T)
+    up_w = torch.randn(C, 3) if up else None
+    up_b = torch.randn(C) if up else None
+    ref = sim.adain_norm(x, gb, 0.2, lens, torch.float16, up_w, up_b)
+    out = ops.adain_norm(x.to(DEV), gb.to(DEV), 0.2, lens.to(DEV), torch.float16,
+                         None if up_w is None else up_w.to(DEV).contiguous(), None if up_b is None else up_b.to(DEV))
+    _close(out, ref, 3e-3, f"adain_norm {shape} up={up}")
+
+
 def test_repeat_and_length_regulate():
     torch.manual_seed(8)
     B, Tt, C = 3, 41, 512

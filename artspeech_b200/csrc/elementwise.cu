@@ -256,10 +256,21 @@ adain_fused_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, i
   const int len = lens ? min(lens[b], T) : T;
   const long long base = (long long)b * T * x_ld;
   float s = 0.f;
-  for (int t = ty; t < len; t += 8) {
-    const float v = cok ? ldany(x, base + (long long)t * x_ld + c, xdt) : 0.f;
-    slab[t * 32 + lane] = v;
-    s += v;
+  // 16 independent row loads in flight per thread: the pass is HBM-latency-bound otherwise
+  // (2 CTAs x 256 threads x 16 x 4 B = 32 KB outstanding per SM)
+  constexpr int ADF_U = 16;
+  for (int t0 = ty; t0 < len; t0 += 8 * ADF_U) {
+    float v[ADF_U];
+#pragma unroll
+    for (int u = 0; u < ADF_U; ++u) {
+      const int t = t0 + 8 * u;
+      v[u] = (cok && t < len) ? ldany(x, base + (long long)t * x_ld + c, xdt) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < ADF_U; ++u) {
+      const int t = t0 + 8 * u;
+      if (t < len) { slab[t * 32 + lane] = v[u]; s += v[u]; }
+    }
   }
   red[ty][lane] = s;
   __syncthreads();
@@ -269,6 +280,7 @@ adain_fused_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, i
   const float mean = len > 0 ? tot / len : 0.f;
   __syncthreads();
   float q = 0.f;
+#pragma unroll 8
   for (int t = ty; t < len; t += 8) { const float d = slab[t * 32 + lane] - mean; q += d * d; }
   red[ty][lane] = q;
   __syncthreads();

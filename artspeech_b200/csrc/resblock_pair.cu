@@ -22,13 +22,16 @@
 //
 // HBM traffic per pair: (1 + halo) reads + 1 write of the tensor instead of 12.  Weights stay
 // resident in shared memory when they fit, otherwise they stream from L2 through an mbarrier ring.
-// Warp roles (384 threads, one CTA per SM): 0 = activation-tile TMA producer, 1 = MMA issuer,
-// 2 = weight TMA producer + TMEM allocator, 3 = second MMA issuer, 4-7 = warpgroup 0, 8-11 = warpgroup 1.
+// Warp roles (640 threads, one CTA per SM): 0 = activation-tile TMA producer, 1 = MMA issuer,
+// 2 = weight TMA producer + TMEM allocator, 3 = second MMA issuer, 4-11 = stage-1 epilogue group (one warp per
+// 32 rows of each M-tile), 12-19 = stage-2 epilogue group.  A lone warp per scheduler converts ~0.3
+// instructions per clock: with 4 + 4 epilogue warps the kernel was epilogue-bound (~7 us per 256-row tile at
+// C = 128, independent of k), so each group got a warp per (M-tile, TMEM lane quadrant).
 #include "tc_util.cuh"
 
 namespace asb {
 
-constexpr int RP_THREADS = 384;
+constexpr int RP_THREADS = 640;
 
 struct PairArgs {
   int B, L, tiles_per_item, total_tiles;
@@ -57,7 +60,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 template <bool BF16>
 __device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
   if (BF16) { a = __uint_as_float(u << 16); b = __uint_as_float(u & 0xFFFF0000u); return; }
@@ -78,7 +81,7 @@ __host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int 
   const uint32_t nres = (stream1 ? 0 : k * KCH) + (stream2 ? 0 : k * KCH);
   s.ring_off = s.wres_off + nres * WBLK;
   s.stg_off = s.ring_off + SW * WBLK;
-  s.bias_off = s.stg_off + 4u * NSTG * 32u * RB;
+  s.bias_off = s.stg_off + 8u * NSTG * 32u * RB;
   s.bar_off = s.bias_off + 2u * C * 4u;
   s.total = s.bar_off + 8u * 64u;
   return s;
@@ -120,10 +123,10 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bias_s[i] = i < C ? a.b1[i] : a.b2[i - C];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 2); mbar_init(t_full(i), 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 2); mbar_init(t_full(i), 8); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full(i), 2); mbar_init(d1_empty(i), 4); mbar_init(d2_init(i), 4);
-      mbar_init(d2_full(i), 2); mbar_init(d2_empty(i), 4);
+      mbar_init(d1_full(i), 2); mbar_init(d1_empty(i), 8); mbar_init(d2_init(i), 8);
+      mbar_init(d2_full(i), 2); mbar_init(d2_empty(i), 8);
     }
     mbar_init(wres_full, 1);
     for (int i = 0; i < 16; ++i) { mbar_init(wr_full(i), 1); mbar_init(wr_empty(i), 2); }
@@ -282,9 +285,10 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 8) {
-    // ===== warpgroup 0: seed D2 with residual + bias2, then epilogue 1 (D1 -> stage-2 operand) =====
+  } else if (warp >= 4 && warp < 12) {
+    // ===== stage-1 group: seed D2 with residual + bias2, then epilogue 1 (D1 -> stage-2 operand) =====
     const int q = warp & 3;
+    const int mt = (warp - 4) >> 2;      // this warp's M-tile
     const float slope = a.slope, inv_slope = a.inv_slope;
     for (int i = 0; i < n_local; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
@@ -297,8 +301,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
       mbar_wait(x_full(xb), (uint32_t)(i / NX) & 1u);
       mbar_wait(d2_empty(db), ((uint32_t)(i / ND) & 1u) ^ 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
+      {
         const uint32_t arow = (uint32_t)(mt * 128 + q * 32 + lane + a.p1 + a.p2);
         const uint32_t swz = (BKC == 64) ? (arow & 7u) : ((arow >> 1) & 3u);
         const uint32_t rbase = xa + arow * RB;
@@ -328,9 +331,8 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
 
       mbar_wait(d1_full(db), (uint32_t)(i / ND) & 1u);
       tc_fence_after();
-      wg_sync(1);   // every warp of the group has read its residual rows: the tile may be overwritten
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
+      group_sync(1);   // every warp of the group has read its residual rows: the tile may be overwritten
+      {
         const uint32_t m = (uint32_t)(mt * 128 + q * 32 + lane);
         const int trow = o0 - a.p2 + (int)m;
         const bool valid = trow >= 0 && trow < len_b;
@@ -360,10 +362,11 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
       __syncwarp();
       if (lane == 0) { mbar_arrive(d1_empty(db)); mbar_arrive(t_full(xb)); }
     }
-  } else if (warp >= 8) {
-    // ===== warpgroup 1: epilogue 2 (D2 -> other branches, scale, mask, activation -> TMA store) =====
+  } else if (warp >= 12) {
+    // ===== stage-2 group: epilogue 2 (D2 -> other branches, scale, mask, activation -> TMA store) =====
     const int q = warp & 3;
-    const uint32_t stg0 = base + sp.stg_off + (uint32_t)q * a.NSTG * 32u * RB;
+    const int mt = (warp - 12) >> 2;     // this warp's M-tile
+    const uint32_t stg0 = base + sp.stg_off + (uint32_t)(warp - 12) * a.NSTG * 32u * RB;
     const uint32_t swz = (BKC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
     const float scale = a.out_scale, aslope = a.out_slope_eff;
     const bool has_res = a.res2 != nullptr || a.res3 != nullptr;
@@ -377,8 +380,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
       if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
       mbar_wait(d2_full(db), (uint32_t)(i / ND) & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
+      {
         const int o = mt * 128 + q * 32 + lane;
         const int grow = o0 + o;
         const bool masked = grow >= len_b;
@@ -517,7 +519,8 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   const size_t cap = 227 * 1024 - 1024;
   const size_t nblk = (size_t)k * KCH;
   int best_found = 0;
-  for (int mode = 0; mode < 3 && !best_found; ++mode) {   // 0: resident, 1: conv1 streamed, 2: both streamed
+  const int mode_lo = env_int("ASB_PAIR_MODE", 0);
+  for (int mode = mode_lo; mode < 3 && !best_found; ++mode) {   // 0: resident, 1: conv1 streamed, 2: both streamed
     a.stream1 = mode >= 1; a.stream2 = mode >= 2;
     for (int nx = 2; nx >= 1 && !best_found; --nx) {
       if (mode == 0 && nx == 1) continue;                 // prefer streaming conv1 over a single buffer
@@ -530,7 +533,7 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
         while (a.SW < 16 && a.SW < want && pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW + 1, a.stream1, a.stream2).total <= cap) ++a.SW;
       }
       if (pair_smem(C, a.HA, k, a.NX, 2, a.SW, a.stream1, a.stream2).total <= cap) a.NSTG = 2;
-      while (a.NX < 3 && mode == 0 && pair_smem(C, a.HA, k, a.NX + 1, a.NSTG, a.SW, a.stream1, a.stream2).total <= cap) ++a.NX;
+      while (a.NX < 3 && mode <= 1 && pair_smem(C, a.HA, k, a.NX + 1, a.NSTG, a.SW, a.stream1, a.stream2).total <= cap) ++a.NX;
     }
   }
   if (!best_found) {
@@ -539,9 +542,11 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   }
   // tuning overrides (tools/prof_pair.py)
   a.NX = env_int("ASB_PAIR_NX", a.NX); a.NSTG = env_int("ASB_PAIR_NSTG", a.NSTG); a.SW = env_int("ASB_PAIR_SW", a.SW);
-  a.pipelined = (a.ND == 2 && a.NX >= 2 && !a.stream1 && !a.stream2) ? 1 : 0;
+  // pipelined issue order needs two accumulator sets and two tiles in flight; with only conv1 streamed the
+  // ring is still consumed in tile order (stage 1 of tile 0, 1, 2, ...), with conv2 streamed it is not
+  a.pipelined = (a.ND == 2 && a.NX >= 2 && !a.stream2) ? 1 : 0;
   a.pipelined = env_int("ASB_PAIR_PIPE", a.pipelined);
-  if (a.stream1 || a.stream2 || a.ND < 2 || a.NX < 2) a.pipelined = 0;
+  if (a.stream2 || a.ND < 2 || a.NX < 2) a.pipelined = 0;
   const PairSmem sp = pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2);
   ASB_REQUIRE(sp.total <= cap && a.NX >= 1 && a.NX <= 4 && a.NSTG >= 1 && a.NSTG <= 2 && a.SW <= 16 &&
                   (!(a.stream1 || a.stream2) || a.SW >= 2),

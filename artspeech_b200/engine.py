@@ -141,22 +141,31 @@ def shard_utterances(costs: Sequence[float], world_size: int) -> List[List[int]]
     return shards
 
 
-def gather_waveforms(wav: torch.Tensor, lengths: torch.Tensor, dst: int = 0, group=None):
+def gather_waveforms(wav: torch.Tensor, lengths: torch.Tensor, dst: int = 0, group=None, shapes=None):
     """Gather per-rank ``wav`` [B_r, S_r] (+ sample ``lengths`` [B_r]) on ``dst``.
 
     Ranks may hold different batch sizes / paddings: sizes are all-gathered first, payloads are
-    padded to the common maximum for one ``gather``.  Works with NCCL (GPU) and gloo (CPU tests).
+    padded to the common maximum for one ``gather``.  ``shapes`` (list of ``(B_r, S_r)`` per rank, known on
+    the host — e.g. from ``shard_utterances``) skips that exchange and its host synchronisation, which keeps
+    a pipelined engine asynchronous.  Works with NCCL (GPU) and gloo (CPU tests).
     Returns (list of [B_r, S_r] tensors, list of lengths) on ``dst``, (None, None) elsewhere."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    shape = torch.tensor([wav.shape[0], wav.shape[1]], dtype=torch.int64, device=wav.device)
-    shapes = [torch.zeros_like(shape) for _ in range(world)]
-    dist.all_gather(shapes, shape, group=group)
-    shapes = [tuple(int(v) for v in s.tolist()) for s in shapes]
+    if shapes is None:
+        shape = torch.tensor([wav.shape[0], wav.shape[1]], dtype=torch.int64, device=wav.device)
+        gathered = [torch.zeros_like(shape) for _ in range(world)]
+        dist.all_gather(gathered, shape, group=group)
+        shapes = [tuple(int(v) for v in s.tolist()) for s in gathered]
+    else:
+        shapes = [tuple(int(v) for v in s) for s in shapes]
+        assert len(shapes) == world and shapes[rank] == tuple(wav.shape)
     Bm, Sm = max(s[0] for s in shapes), max(s[1] for s in shapes)
-    pad = torch.zeros(Bm, Sm, dtype=wav.dtype, device=wav.device)
-    pad[:wav.shape[0], :wav.shape[1]] = wav
+    if tuple(wav.shape) == (Bm, Sm) and wav.is_contiguous():
+        pad = wav
+    else:
+        pad = torch.zeros(Bm, Sm, dtype=wav.dtype, device=wav.device)
+        pad[:wav.shape[0], :wav.shape[1]] = wav
     lpad = torch.zeros(Bm, dtype=torch.int64, device=wav.device)
     lpad[:lengths.shape[0]] = lengths.to(torch.int64)
     if rank == dst:

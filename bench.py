@@ -33,7 +33,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_PER_GPU, TT, TR, SUM_DUR = 16, 150, 240, 400
+B_PER_GPU, TT, TR, SUM_DUR = int(os.environ.get("ASB_BENCH_B", "16")), 150, 240, 400   # env override: experiments only
 FRAMES = 2 * SUM_DUR                                   # mel frames per utterance
 AUDIO_S_PER_UTT = FRAMES * 300 / 24000.0               # 10.0 s
 VOCODER_FLOP_PER_FRAME = 623.7e6
@@ -191,6 +191,7 @@ def run_ours(args):
     wav_hs = [torch.empty(B_PER_GPU, FRAMES * 300, dtype=torch.float32).pin_memory() for _ in range(max(args.pipeline, 1))]
     wav_h = wav_hs[0]
     calls = [0]
+    wav_lens_d = torch.full((B_PER_GPU,), FRAMES * 300, device=dev)
 
     def step_resident():
         return syn.synthesize(tok_d, tok_lens, mel_d, mel_lens, dur)
@@ -203,7 +204,7 @@ def run_ours(args):
         # the waveforms are produced on the engine's stream for this call: gather / D2H follow on that stream
         with torch.cuda.stream(syn.last_stream):
             if world > 1:
-                gathered, _ = engine.gather_waveforms(wav, torch.full((wav.shape[0],), wav.shape[1], device=dev))
+                gathered, _ = engine.gather_waveforms(wav, wav_lens_d, shapes=[tuple(wav.shape)] * world)
             wav_hs[calls[0] % len(wav_hs)].copy_(wav, non_blocking=True)
         return wav
 

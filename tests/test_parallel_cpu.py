@@ -45,9 +45,12 @@ def _worker(rank, world, port, q):
             wav[r, :costs[i] * 3] = i + 1
             lens[r] = costs[i] * 3
         wavs, lns = engine.gather_waveforms(wav, lens, dst=0)
+        # host-known shapes (from the same deterministic sharding): no size exchange, same result
+        shards = engine.shard_utterances(costs, world)
+        shapes = [(len(sh), max([costs[i] * 3 for i in sh], default=1)) for sh in shards]
+        wavs2, lns2 = engine.gather_waveforms(wav, lens, dst=0, shapes=shapes)
         if rank == 0:
-            shards = engine.shard_utterances(costs, world)
-            ok = True
+            ok = all(torch.equal(a, b) for a, b in zip(wavs, wavs2)) and all(torch.equal(a, b) for a, b in zip(lns, lns2))
             for r in range(world):
                 for row, i in enumerate(shards[r]):
                     n = int(lns[r][row])
@@ -55,7 +58,7 @@ def _worker(rank, world, port, q):
                         bool((wavs[r][row, n:] == 0).all())
             q.put(ok)
         else:
-            assert wavs is None and lns is None
+            assert wavs is None and lns is None and wavs2 is None
     finally:
         dist.destroy_process_group()
 

@@ -18,6 +18,11 @@ __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); 
 // MUFU-based variants for the per-step critical path of the tensor-core kernels (abs error ~1e-6)
 __device__ __forceinline__ float fsigm(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 __device__ __forceinline__ float ftanh(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
+// bare MUFU forms (no range fix-ups: ex2 -> +inf gives rcp -> 0, the correct limit; abs error ~3e-7)
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gsigm(float v) { return mufu_rcp(1.f + mufu_ex2(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float gtanh(float v) { return fmaf(-2.f, mufu_rcp(1.f + mufu_ex2(2.8853900817779268f * v)), 1.f); }
 
 template <int BG>
 __global__ void __launch_bounds__(1024, 1) bilstm_kernel(const float* __restrict__ xproj, long long xp_ld,
@@ -177,24 +182,37 @@ bilstm128_mma_kernel(const float* __restrict__ xproj, long long xp_ld,
       stany(out, ((long long)b * T + e / H) * out_ld + dir * H + (e % H), 0.f, odt);
   }
 
-  auto xp_at = [&](int n, int len, int s, int q, int j) -> float {
-    if (s >= len) return 0.f;
-    const int t = dir == 0 ? s : len - 1 - s;
-    return __ldg(xproj + ((long long)(b0 + n) * T + t) * xp_ld + (long long)dir * G + q * H + j);
-  };
+  // Pointer-walking addressing: per thread two input rows (items n0, n0+1) and two output rows; the gate
+  // (q * H) and unit (j1 = j0 + 8) offsets are compile-time immediates, the step is one pointer bump.
+  // (ncu: the kernel issued ~390 instructions per warp per step, most of them 64-bit address arithmetic,
+  // dtype dispatch and the range checks of __fdividef; the step is issue-bound with 2 warps per scheduler.)
+  const long long step0 = dir == 0 ? xp_ld : -xp_ld, step1 = step0;
+  const float* px0 = xproj + ((long long)(b0 + n0) * T + (dir == 0 ? 0 : max(len0 - 1, 0))) * xp_ld + (long long)dir * G + j0;
+  const float* px1 = xproj + ((long long)(b0 + n0 + 1) * T + (dir == 0 ? 0 : max(len1 - 1, 0))) * xp_ld + (long long)dir * G + j0;
+  const int es = odt == AS_F32 ? 4 : 2;
+  const long long ostep = (dir == 0 ? out_ld : -out_ld) * es;
+  char* po0 = reinterpret_cast<char*>(out) + (((long long)(b0 + n0) * T + (dir == 0 ? 0 : max(len0 - 1, 0))) * out_ld + dir * H + j0) * es;
+  char* po1 = reinterpret_cast<char*>(out) + (((long long)(b0 + n0 + 1) * T + (dir == 0 ? 0 : max(len1 - 1, 0))) * out_ld + dir * H + j0) * es;
   // input projections are prefetched PF steps ahead (register ring; the loop is unrolled by PF so
   // the ring slots are compile-time): the L2 latency of the 16 scattered loads hides behind PF steps.
   constexpr int PF = 4;
   float xn[PF][4][4];
   auto fetch = [&](float (&dst)[4][4], int s) {
+    const bool v0 = s < len0, v1 = s < len1;
+    const float* p0 = px0 + (long long)s * step0;
+    const float* p1 = px1 + (long long)s * step1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      dst[q][0] = xp_at(n0, len0, s, q, j0); dst[q][1] = xp_at(n0 + 1, len1, s, q, j0);
-      dst[q][2] = xp_at(n0, len0, s, q, j1); dst[q][3] = xp_at(n0 + 1, len1, s, q, j1);
+      dst[q][0] = v0 ? __ldg(p0 + q * H) : 0.f;     dst[q][1] = v1 ? __ldg(p1 + q * H) : 0.f;
+      dst[q][2] = v0 ? __ldg(p0 + q * H + 8) : 0.f; dst[q][3] = v1 ? __ldg(p1 + q * H + 8) : 0.f;
     }
   };
 #pragma unroll
   for (int u = 0; u < PF; ++u) fetch(xn[u], u);
+  auto put = [&](char* p, float v) {
+    if (es == 4) *reinterpret_cast<float*>(p) = v;
+    else *reinterpret_cast<uint16_t*>(p) = to16(v, odt);
+  };
 
   for (int s0 = 0; s0 < maxlen; s0 += PF) {
 #pragma unroll
@@ -218,24 +236,22 @@ bilstm128_mma_kernel(const float* __restrict__ xproj, long long xp_ld,
       for (int q = 0; q < 4; ++q) mma16816(acc[q], afrag[q][ks], bb0, bb1);
     }
     // cell update in registers (fp32): element e -> (unit, batch) = (j0,n0) (j0,n0+1) (j1,n0) (j1,n0+1)
+    const bool live0 = s < len0, live1 = s < len1;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int n = n0 + (e & 1), j = (e < 2) ? j0 : j1;
-      const int len = (e & 1) ? len1 : len0;
-      if (s < len) {
-        const float ig = fsigm(acc[0][e]), fg = fsigm(acc[1][e]), gg = ftanh(acc[2][e]), og = fsigm(acc[3][e]);
+      if ((e & 1) ? live1 : live0) {
+        const float ig = gsigm(acc[0][e]), fg = gsigm(acc[1][e]), gg = gtanh(acc[2][e]), og = gsigm(acc[3][e]);
         c[e] = fg * c[e] + ig * gg;
-        const float hval = og * ftanh(c[e]);
+        const float hval = og * gtanh(c[e]);
         hn[n * L128_HP + j] = __float2half_rn(hval);
-        const int t = dir == 0 ? s : len - 1 - s;
-        stany(out, ((long long)(b0 + n) * T + t) * out_ld + dir * H + j, hval, odt);
+        put(((e & 1) ? po1 : po0) + (long long)s * ostep + ((e < 2) ? 0 : 8 * es), hval);
       }
     }
     __syncthreads();
    }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // H = 256 (duration predictor, JDCNet): W_hh in fp16 is 512 KB, more than one SM can hold.  A
@@ -371,9 +387,9 @@ bilstm256_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
         const int len = e ? len1 : len0;
         hv[e] = 0.f;
         if (s < len) {
-          const float ig = fsigm(acc[0][e]), fg = fsigm(acc[0][2 + e]), gg = ftanh(acc[1][e]), og = fsigm(acc[1][2 + e]);
+          const float ig = gsigm(acc[0][e]), fg = gsigm(acc[0][2 + e]), gg = gtanh(acc[1][e]), og = gsigm(acc[1][2 + e]);
           c[e] = fg * c[e] + ig * gg;
-          hv[e] = og * ftanh(c[e]);
+          hv[e] = og * gtanh(c[e]);
           const int t = dir == 0 ? s : len - 1 - s;
           stany(out, ((long long)(b0 + n0 + e) * T + t) * out_ld + dir * H + unit, hv[e], odt);
         }

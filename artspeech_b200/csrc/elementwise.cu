@@ -3,7 +3,7 @@
 // small-Cin direct convolution, depthwise convolution, pooling, layout changes.
 // All of them are coalesced along the channel axis of the channels-last activations and
 // vectorised where the row pitch allows it; reductions use warp shuffles.
-#include "common.cuh"
+#include "tc_util.cuh"
 
 namespace asb {
 
@@ -240,79 +240,257 @@ adain_apply_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int 
 // item, keeps the whole [T, 32] fp32 slab in shared memory (T <= 1536), computes the exact two-pass
 // mean / biased variance from it and writes the activated tensor.  Replaces the stats + apply launches
 // (3 reads + 1 write of the tensor -> 1 read + 1 write).
-constexpr int ADF_MAX_T = 1536;
+constexpr int ADF_CS = 4;                 // CTAs per cluster: the T axis of one (item, 32-channel block) is split 4 ways
+constexpr int ADF_MAX_TR = 1536;          // rows per CTA that fit in shared memory -> T <= 6144
 
-template <bool UP>
-__global__ void __launch_bounds__(256)
-adain_fused_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, int C,
+// 4 consecutive channels of one row: 16-byte (fp32) or 8-byte (16-bit) load, dtype resolved at compile time
+template <int XDT>
+__device__ __forceinline__ float4 adf_load4(const void* x, long long off) {
+  if (XDT == AS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + off));
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + off));
+  return make_float4(from16(uint16_t(u.x & 0xFFFF), XDT), from16(uint16_t(u.x >> 16), XDT),
+                     from16(uint16_t(u.y & 0xFFFF), XDT), from16(uint16_t(u.y >> 16), XDT));
+}
+__device__ __forceinline__ uint32_t adf_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float adf_ld_peer(const float* p, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ void adf_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// One thread-block CLUSTER of 4 CTAs per (item, 32-channel block); CTA r owns rows [r*TR, (r+1)*TR) and keeps
+// them in shared memory.  Exact two-pass statistics: per-CTA partial sums, exchanged through distributed
+// shared memory (ld.shared::cluster) around two cluster barriers; then each CTA normalises and writes its
+// rows.  Small slabs (28 KB at T = 800) put 8 CTAs on an SM, so loads, reductions and stores of different
+// CTAs overlap and the pass streams HBM (one read + one write of the tensor).
+// Thread layout: warp w, lane -> (row-in-group r4 = lane >> 3, channel quad c4 = lane & 7): one warp
+// instruction moves 4 rows x 128 B; ADF_U independent 16-byte loads per thread are in flight.
+template <bool UP, int XDT>
+__global__ void __cluster_dims__(ADF_CS, 1, 1) __launch_bounds__(256)
+adain_fused_kernel(const void* __restrict__ x, long long x_ld, int T, int TR, int C,
                    const float* __restrict__ gb, long long gb_ld, float eps, float slope,
                    const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
                    void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
-  extern __shared__ float slab[];            // [T][32]
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int b = blockIdx.y, c = blockIdx.x * 32 + lane;
+  extern __shared__ __align__(16) float slab[];            // [TR][32]
+  __shared__ float red[8][32];
+  __shared__ float part[2][32];                            // this CTA's partial sum / partial squared deviation
+  constexpr int ADF_U = 8;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r4 = lane >> 3, c4 = lane & 7;
+  const uint32_t rank = adf_cluster_rank();
+  const int b = blockIdx.y, c = (blockIdx.x / ADF_CS) * 32 + 4 * c4;
+  const bool cok = c < C;                                   // C % 4 == 0: a quad is all-in or all-out
+  const int len = lens ? min(lens[b], T) : T;
+  const int t_lo = (int)rank * TR, t_hi = min(len, t_lo + TR);   // valid rows of this CTA
+  const long long base = (long long)b * T * x_ld + c;
+  const int row0 = t_lo + w * 4 + r4;                       // this thread's rows: row0 + 32 * i
+
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = row0; t0 < t_hi; t0 += 32 * ADF_U) {
+    float4 v[ADF_U];
+#pragma unroll
+    for (int u = 0; u < ADF_U; ++u) {
+      const int t = t0 + 32 * u;
+      v[u] = (cok && t < t_hi) ? adf_load4<XDT>(x, base + (long long)t * x_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < ADF_U; ++u) {
+      const int t = t0 + 32 * u;
+      if (t < t_hi) {
+        *reinterpret_cast<float4*>(slab + (t - t_lo) * 32 + 4 * c4) = v[u];
+        s4.x += v[u].x; s4.y += v[u].y; s4.z += v[u].z; s4.w += v[u].w;
+      }
+    }
+  }
+  // CTA-level reduction (4 row lanes of a warp, then 8 warps) into part[which]; then the cluster-level sum
+  auto reduce_cluster = [&](float4 p, int which) -> float4 {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      p.x += __shfl_xor_sync(0xffffffffu, p.x, o); p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
+      p.z += __shfl_xor_sync(0xffffffffu, p.z, o); p.w += __shfl_xor_sync(0xffffffffu, p.w, o);
+    }
+    if (r4 == 0) *reinterpret_cast<float4*>(&red[w][4 * c4]) = p;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+      part[which][threadIdx.x] = t;
+    }
+    adf_cluster_sync();                                     // every CTA's partial is published (also a CTA barrier)
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (uint32_t r = 0; r < ADF_CS; ++r) {
+      tot.x += adf_ld_peer(&part[which][4 * c4], r);     tot.y += adf_ld_peer(&part[which][4 * c4 + 1], r);
+      tot.z += adf_ld_peer(&part[which][4 * c4 + 2], r); tot.w += adf_ld_peer(&part[which][4 * c4 + 3], r);
+    }
+    return tot;
+  };
+  const float inv_len = len > 0 ? 1.f / len : 0.f;
+  float4 mean = reduce_cluster(s4, 0);
+  mean.x *= inv_len; mean.y *= inv_len; mean.z *= inv_len; mean.w *= inv_len;
+  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = row0; t < t_hi; t += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(slab + (t - t_lo) * 32 + 4 * c4);
+    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+    q4.x += dx * dx; q4.y += dy * dy; q4.z += dz * dz; q4.w += dw * dw;
+  }
+  const float4 var = reduce_cluster(q4, 1);
+  adf_cluster_sync();                                       // peers have read this CTA's partials: it may exit later
+  if (!cok) return;
+  const float4 rstd = make_float4(rsqrtf(var.x * inv_len + eps), rsqrtf(var.y * inv_len + eps),
+                                  rsqrtf(var.z * inv_len + eps), rsqrtf(var.w * inv_len + eps));
+  if (stats_out != nullptr && rank == 0 && threadIdx.x < 8) {
+    float* so = stats_out + ((long long)b * C + c) * 2;
+    so[0] = mean.x; so[1] = rstd.x; so[2] = mean.y; so[3] = rstd.y; so[4] = mean.z; so[5] = rstd.z; so[6] = mean.w; so[7] = rstd.w;
+  }
+  const float4 g = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + c);
+  const float4 be = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + C + c);
+  const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
+  auto act4 = [&](float4 v) -> float4 {
+    v.x = (v.x - mean.x) * sc.x + be.x; v.y = (v.y - mean.y) * sc.y + be.y;
+    v.z = (v.z - mean.z) * sc.z + be.z; v.w = (v.w - mean.w) * sc.w + be.w;
+    v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+    v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+    return v;
+  };
+  auto act_at = [&](int t) -> float4 {                      // t in this CTA's range, or its first row past it
+    if (t >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < t_lo + TR) return act4(*reinterpret_cast<const float4*>(slab + (t - t_lo) * 32 + 4 * c4));
+    return act4(adf_load4<XDT>(x, base + (long long)t * x_ld));   // the next CTA's first row (pool variant only)
+  };
+  const int t_end = min(T, t_lo + TR);                      // rows this CTA writes (zeros beyond len)
+  if (!UP) {
+#pragma unroll 4
+    for (int t = row0; t < t_end; t += 32) st4any(out, ((long long)b * T + t) * out_ld + c, act_at(t), odt);
+  } else {
+    float w0[4], w1[4], w2[4], ub[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
+    for (int t = row0; t < t_end; t += 32) {
+      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
+      if (t < len) {
+        const float4 a0 = act_at(t), a1 = act_at(t + 1);
+        ev = make_float4(a0.x * w1[0] + ub[0], a0.y * w1[1] + ub[1], a0.z * w1[2] + ub[2], a0.w * w1[3] + ub[3]);
+        od = make_float4(a0.x * w2[0] + a1.x * w0[0] + ub[0], a0.y * w2[1] + a1.y * w0[1] + ub[1],
+                         a0.z * w2[2] + a1.z * w0[2] + ub[2], a0.w * w2[3] + a1.w * w0[3] + ub[3]);
+      }
+      st4any(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
+      st4any(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+    }
+  }
+}
+
+// TMA variant for fp32 input and T <= 1760: the whole [T, 32-channel] slab of a CTA is fetched by a handful
+// of bulk tensor copies issued by one thread (100 KB in flight per CTA at T = 800, no registers involved),
+// so the read phase runs at HBM speed instead of at (loads in flight per thread) / latency.
+constexpr int ADT_MAX_ROWS = 1760;
+
+template <bool UP>
+__global__ void __launch_bounds__(256)
+adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbox, int C,
+                 const float* __restrict__ gb, long long gb_ld, float eps, float slope,
+                 const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
+                 void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
+  extern __shared__ __align__(128) float slab_raw[];
+  __shared__ float red[8][32];
+  __shared__ __align__(8) unsigned long long bar_storage;
+  float* slab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(slab_raw) + 127) & ~uintptr_t(127));   // [nbox*BR][32]
+  const uint32_t bar = smem_u32(&bar_storage);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r4 = lane >> 3, c4 = lane & 7;
+  const int b = blockIdx.y, cb = blockIdx.x * 32, c = cb + 4 * c4;
   const bool cok = c < C;
   const int len = lens ? min(lens[b], T) : T;
-  const long long base = (long long)b * T * x_ld;
-  float s = 0.f;
-  // 16 independent row loads in flight per thread: the pass is HBM-latency-bound otherwise
-  // (2 CTAs x 256 threads x 16 x 4 B = 32 KB outstanding per SM)
-  constexpr int ADF_U = 16;
-  for (int t0 = ty; t0 < len; t0 += 8 * ADF_U) {
-    float v[ADF_U];
-#pragma unroll
-    for (int u = 0; u < ADF_U; ++u) {
-      const int t = t0 + 8 * u;
-      v[u] = (cok && t < len) ? ldany(x, base + (long long)t * x_ld + c, xdt) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < ADF_U; ++u) {
-      const int t = t0 + 8 * u;
-      if (t < len) { slab[t * 32 + lane] = v[u]; s += v[u]; }
-    }
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, (uint32_t)nbox * BR * 128u);
+    for (int k = 0; k < nbox; ++k) tma_load_3d(smem_u32(slab) + (uint32_t)k * BR * 128u, &tmx, bar, cb, k * BR, b);
   }
-  red[ty][lane] = s;
   __syncthreads();
-  float tot = 0.f;
+  mbar_wait(bar, 0);
+  const int row0 = w * 4 + r4;
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = row0; t < len; t += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(slab + t * 32 + 4 * c4);
+    s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+  }
+  auto reduce4 = [&](float4 p) -> float4 {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i][lane];
-  const float mean = len > 0 ? tot / len : 0.f;
-  __syncthreads();
-  float q = 0.f;
-#pragma unroll 8
-  for (int t = ty; t < len; t += 8) { const float d = slab[t * 32 + lane] - mean; q += d * d; }
-  red[ty][lane] = q;
-  __syncthreads();
-  float var = 0.f;
+    for (int o = 8; o <= 16; o <<= 1) {
+      p.x += __shfl_xor_sync(0xffffffffu, p.x, o); p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
+      p.z += __shfl_xor_sync(0xffffffffu, p.z, o); p.w += __shfl_xor_sync(0xffffffffu, p.w, o);
+    }
+    __syncthreads();
+    if (r4 == 0) *reinterpret_cast<float4*>(&red[w][4 * c4]) = p;
+    __syncthreads();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) var += red[i][lane];
-  var = len > 0 ? var / len : 0.f;
-  const float rstd = rsqrtf(var + eps);
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = *reinterpret_cast<const float4*>(&red[i][4 * c4]);
+      t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+    }
+    return t;
+  };
+  const float inv_len = len > 0 ? 1.f / len : 0.f;
+  float4 mean = reduce4(s4);
+  mean.x *= inv_len; mean.y *= inv_len; mean.z *= inv_len; mean.w *= inv_len;
+  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = row0; t < len; t += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(slab + t * 32 + 4 * c4);
+    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+    q4.x += dx * dx; q4.y += dy * dy; q4.z += dz * dz; q4.w += dw * dw;
+  }
+  const float4 var = reduce4(q4);
   if (!cok) return;
-  if (stats_out != nullptr && ty == 0) {
-    stats_out[((long long)b * C + c) * 2] = mean;
-    stats_out[((long long)b * C + c) * 2 + 1] = rstd;
+  const float4 rstd = make_float4(rsqrtf(var.x * inv_len + eps), rsqrtf(var.y * inv_len + eps),
+                                  rsqrtf(var.z * inv_len + eps), rsqrtf(var.w * inv_len + eps));
+  if (stats_out != nullptr && threadIdx.x < 8) {
+    float* so = stats_out + ((long long)b * C + c) * 2;
+    so[0] = mean.x; so[1] = rstd.x; so[2] = mean.y; so[3] = rstd.y; so[4] = mean.z; so[5] = rstd.z; so[6] = mean.w; so[7] = rstd.w;
   }
-  const float sc = rstd * (1.f + gb[(long long)b * gb_ld + c]), be = gb[(long long)b * gb_ld + C + c];
-  auto act_at = [&](int t) -> float {
-    if (t >= len) return 0.f;
-    const float v = (slab[t * 32 + lane] - mean) * sc + be;
-    return v > 0.f ? v : v * slope;
+  const float4 g = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + c);
+  const float4 be = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + C + c);
+  const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
+  auto act_at = [&](int t) -> float4 {
+    if (t >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = *reinterpret_cast<const float4*>(slab + t * 32 + 4 * c4);
+    v.x = (v.x - mean.x) * sc.x + be.x; v.y = (v.y - mean.y) * sc.y + be.y;
+    v.z = (v.z - mean.z) * sc.z + be.z; v.w = (v.w - mean.w) * sc.w + be.w;
+    v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+    v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+    return v;
   };
   if (!UP) {
-    for (int t = ty; t < T; t += 8) stany(out, ((long long)b * T + t) * out_ld + c, act_at(t), odt);
+#pragma unroll 4
+    for (int t = row0; t < T; t += 32) st4any(out, ((long long)b * T + t) * out_ld + c, act_at(t), odt);
   } else {
-    const float w0 = up_w[c * 3], w1 = up_w[c * 3 + 1], w2 = up_w[c * 3 + 2], ub = up_b[c];
-    for (int t = ty; t < T; t += 8) {
-      float ev = 0.f, od = 0.f;
+    float w0[4], w1[4], w2[4], ub[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
+    for (int t = row0; t < T; t += 32) {
+      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
       if (t < len) {
-        const float a0 = act_at(t), a1 = act_at(t + 1);
-        ev = a0 * w1 + ub;
-        od = a0 * w2 + a1 * w0 + ub;
+        const float4 a0 = act_at(t), a1 = act_at(t + 1);
+        ev = make_float4(a0.x * w1[0] + ub[0], a0.y * w1[1] + ub[1], a0.z * w1[2] + ub[2], a0.w * w1[3] + ub[3]);
+        od = make_float4(a0.x * w2[0] + a1.x * w0[0] + ub[0], a0.y * w2[1] + a1.y * w0[1] + ub[1],
+                         a0.z * w2[2] + a1.z * w0[2] + ub[2], a0.w * w2[3] + a1.w * w0[3] + ub[3]);
       }
-      stany(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
-      stany(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+      st4any(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
+      st4any(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
     }
   }
 }
@@ -825,19 +1003,65 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
   if ((long long)B * T * C == 0) return AS_OK;
   ASB_REQUIRE(x && gb && out && stats && dt_ok(x_dtype), AS_ERR_SHAPE, "as_adain_norm_apply: bad argument");
   ASB_REQUIRE(!up_w || up_b, AS_ERR_SHAPE, "as_adain_norm_apply: up_w without up_b");
-  if (T <= ADF_MAX_T) {
-    const size_t smem = (size_t)T * 32 * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-      ASB_CUDA(cudaFuncSetAttribute(adain_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADF_MAX_T * 32 * 4));
-      ASB_CUDA(cudaFuncSetAttribute(adain_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADF_MAX_T * 32 * 4));
-      attr = true;
+  auto row_ok = [](const void* ptr, long long ld, int dt) {
+    const int es = dt == AS_F32 ? 4 : 2;
+    return (reinterpret_cast<uintptr_t>(ptr) % (4 * es)) == 0 && ((ld * es) % (4 * es)) == 0;
+  };
+  static const bool no_tma = getenv("ASB_ADAIN_NO_TMA") != nullptr;
+  if (!no_tma && x_dtype == AS_F32 && T <= ADT_MAX_ROWS && (C % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (x_ld % 4) == 0 && [&] { const int es = out_dtype == AS_F32 ? 4 : 2;
+                              return (reinterpret_cast<uintptr_t>(out) % (4 * es)) == 0 && ((out_ld * es) % (4 * es)) == 0; }() &&
+      (reinterpret_cast<uintptr_t>(gb) & 15) == 0 && (gb_ld % 4) == 0 && check_arch() == AS_OK) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc) {
+      const int nbox = (T + 255) / 256;
+      const int BR = ((T + nbox - 1) / nbox + 7) / 8 * 8;
+      CUtensorMap tmx;
+      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)x_ld * 4, (cuuint64_t)x_ld * 4 * T};
+      cuuint32_t box[3] = {32, (cuuint32_t)BR, 1};
+      cuuint32_t es3[3] = {1, 1, 1};
+      if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        const size_t smem = (size_t)nbox * BR * 128 + 128;
+        static bool attr = false;
+        if (!attr) {
+          ASB_CUDA(cudaFuncSetAttribute(adain_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+          ASB_CUDA(cudaFuncSetAttribute(adain_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+          attr = true;
+        }
+        dim3 grid(cdiv(C, 32), (unsigned)B);
+        if (up_w) adain_tma_kernel<true><<<grid, 256, smem, ST(stream)>>>(tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
+                                                                         out, out_dtype, out_ld, stats);
+        else adain_tma_kernel<false><<<grid, 256, smem, ST(stream)>>>(tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
+                                                                     out, out_dtype, out_ld, stats);
+        ASB_CUDA(cudaGetLastError());
+        return AS_OK;
+      }
     }
-    dim3 grid(cdiv(C, 32), (unsigned)B);
-    if (up_w) adain_fused_kernel<true><<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, T, C, gb, gb_ld, eps, slope, lens, up_w,
-                                                                       up_b, out, out_dtype, out_ld, stats);
-    else adain_fused_kernel<false><<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, T, C, gb, gb_ld, eps, slope, lens, up_w,
-                                                                   up_b, out, out_dtype, out_ld, stats);
+  }
+  const int TR = ((T + ADF_CS - 1) / ADF_CS + 31) / 32 * 32;     // rows per CTA of the cluster
+  if (TR <= ADF_MAX_TR && (C % 4) == 0 && row_ok(x, x_ld, x_dtype) && row_ok(out, out_ld, out_dtype) &&
+      (reinterpret_cast<uintptr_t>(gb) & 15) == 0 && (gb_ld % 4) == 0) {
+    const size_t smem = (size_t)TR * 32 * sizeof(float);
+    dim3 grid(cdiv(C, 32) * ADF_CS, (unsigned)B);
+#define ADF_LAUNCH(UP_, XDT_)                                                                                  \
+  do {                                                                                                         \
+    static bool attr = false;                                                                                  \
+    if (!attr) {                                                                                               \
+      ASB_CUDA(cudaFuncSetAttribute(adain_fused_kernel<UP_, XDT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    ADF_MAX_TR * 32 * 4));                                                      \
+      attr = true;                                                                                             \
+    }                                                                                                          \
+    adain_fused_kernel<UP_, XDT_><<<grid, 256, smem, ST(stream)>>>(x, x_ld, T, TR, C, gb, gb_ld, eps, slope, lens, up_w, \
+                                                                   up_b, out, out_dtype, out_ld, stats);       \
+  } while (0)
+    if (up_w) {
+      if (x_dtype == AS_F32) ADF_LAUNCH(true, AS_F32); else if (x_dtype == AS_F16) ADF_LAUNCH(true, AS_F16); else ADF_LAUNCH(true, AS_BF16);
+    } else {
+      if (x_dtype == AS_F32) ADF_LAUNCH(false, AS_F32); else if (x_dtype == AS_F16) ADF_LAUNCH(false, AS_F16); else ADF_LAUNCH(false, AS_BF16);
+    }
+#undef ADF_LAUNCH
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }

@@ -208,9 +208,12 @@ int as_adain_apply(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int3
                    const int32_t* lens, const float* up_w, const float* up_b, void* out,
                    int32_t out_dtype, int64_t out_ld, void* stream);
 
-/* as_instnorm_stats + as_adain_apply in one launch (one read + one write of the tensor; sequences up
- * to 1536 frames keep their [T, 32-channel] slab in shared memory, longer ones run the two passes).
- * `stats` fp32 [B, C, 2] receives {mean, rstd} (always required: it is the workspace of the long path). */
+/* as_instnorm_stats + as_adain_apply in one launch: one read + one write of the tensor, exact two-pass
+ * statistics from a shared-memory slab.  fp32 input up to 1750 frames: one CTA per (item, 32 channels), the
+ * slab arrives by TMA bulk tensor copies; otherwise (16-bit input, up to 6144 frames) a cluster of 4 CTAs
+ * splits the frames and exchanges partial sums through distributed shared memory; longer sequences run the
+ * two separate passes.  `stats` fp32 [B, C, 2] receives {mean, rstd} (always required: it is the
+ * workspace of the long path). */
 int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t T, int32_t C,
                         const float* gb, int64_t gb_ld, float eps, float slope, const int32_t* lens,
                         const float* up_w, const float* up_b, void* out, int32_t out_dtype,

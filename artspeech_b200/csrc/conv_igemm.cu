@@ -21,6 +21,10 @@
 
 namespace asb {
 
+// conv_cout1.cu: single-output-channel 1-D convolutions are an HBM stream, not a GEMM
+bool conv_cout1_eligible(const as_conv_params* p);
+int conv_cout1_launch(const as_conv_params* p, cudaStream_t st);
+
 // instantiated in conv_inst_*.cu
 extern template int launch_conv<16, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
 extern template int launch_conv<16, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
@@ -129,6 +133,8 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
   ASB_REQUIRE(p->stats == nullptr, AS_ERR_SHAPE, "as_conv_igemm: fused stats not available yet");
   int rc = check_arch();
   if (rc != AS_OK) return rc;
+  static const bool no_cout1 = getenv("ASB_NO_COUT1") != nullptr;
+  if (!no_cout1 && conv_cout1_eligible(p)) return conv_cout1_launch(p, reinterpret_cast<cudaStream_t>(stream));
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return AS_ERR_CUDA;
 

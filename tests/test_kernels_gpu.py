@@ -53,6 +53,25 @@ def test_conv_igemm_1d(shape, dt):
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 1000, 32, 7, 1), (1, 700, 64, 5, 3), (3, 257, 16, 3, 1), (1, 255, 32, 1, 1)])
+def test_conv_single_output_channel(shape, dt):
+    """Cout = 1 convolutions (the vocoder's conv_post + tanh) take the streaming kernel in conv_cout1.cu."""
+    B, T, Cin, k, dil = shape
+    torch.manual_seed(4)
+    x = (torch.randn(B, T, Cin) * 0.5).to(dt)
+    w = torch.randn(k, 1, Cin) / (Cin * k) ** 0.5
+    bias = torch.randn(1)
+    lens = _lens(B, T)
+    pw_c = ops.pack_conv(w, bias, ops.taps_1d(k, dil), dt, "cpu")
+    pw_g = ops.pack_conv(w, bias, ops.taps_1d(k, dil), dt, DEV)
+    ref_raw, ref_act = sim.conv(x, pw_c, scale=0.9, raw=torch.float32, act_out=torch.float32, act=ops.ACT_TANH, lens=lens)
+    raw, act = ops.conv(x.to(DEV), pw_g, scale=0.9, raw=torch.float32, act_out=torch.float32, act=ops.ACT_TANH,
+                        lens=lens.to(DEV))
+    _close(raw, ref_raw, 2e-4, "raw")
+    _close(act, ref_act, 2e-4, "act")
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(2, 700, 64, 3, 1), (2, 1000, 64, 7, 3), (1, 1500, 64, 11, 5), (3, 333, 32, 3, 5),
                                    (2, 2000, 32, 11, 5), (1, 900, 32, 7, 1), (2, 600, 128, 3, 3), (1, 800, 128, 7, 5),
                                    (1, 700, 128, 11, 5), (4, 100, 64, 7, 5), (1, 246, 32, 11, 1), (1, 247, 64, 11, 3)])

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(RA_WARPS * 32)
 relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float* __restrict__ relk,
                         const float* __restrict__ relv, int window, int T, int H,
                         const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ float sm[];
   constexpr int KP = D + 1;                 // padded pitch: conflict-free row reads
   float* kv = sm;                           // [RA_KT][KP]
@@ -171,6 +172,7 @@ conformer_attention_kernel(const float* __restrict__ q, const float* __restrict_
                            const float* __restrict__ v, long long ld, const float* __restrict__ pos,
                            const float* __restrict__ ub, const float* __restrict__ vb, int T, int H,
                            const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -265,6 +267,7 @@ conformer_attention_tiled_kernel(const float* __restrict__ q, const float* __res
                                  const float* __restrict__ v, long long ld, const float* __restrict__ pos,
                                  const float* __restrict__ ub, const float* __restrict__ vb, int T, int H,
                                  const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   constexpr int KS = D + 4;     // padded row stride of the key tile (float4-aligned, conflict-free)
   constexpr int QPW = CT_QT / CT_WARPS;
   extern __shared__ float sm[];
@@ -412,8 +415,8 @@ extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float
     attr = true;
   }
   dim3 grid((T + RA_QT - 1) / RA_QT, H, B);
-  relpos_attention_kernel<128><<<grid, RA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      qkv, qkv_ld, emb_rel_k, emb_rel_v, window, T, H, lens, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(relpos_attention_kernel<128>, grid, RA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream), 
+      qkv, qkv_ld, emb_rel_k, emb_rel_v, window, T, H, lens, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -437,8 +440,8 @@ extern "C" int as_conformer_attention(const float* q, const float* k, const floa
         attr_t = true;
       }
       dim3 grid((T + CT_QT - 1) / CT_QT, H, B);
-      conformer_attention_tiled_kernel<64><<<grid, CT_WARPS * 32, smem_t, reinterpret_cast<cudaStream_t>(stream)>>>(
-          q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld);
+      ASB_CUDA(launch_k(conformer_attention_tiled_kernel<64>, grid, CT_WARPS * 32, smem_t, reinterpret_cast<cudaStream_t>(stream), 
+          q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld));
       ASB_CUDA(cudaGetLastError());
       return AS_OK;
     }
@@ -451,8 +454,8 @@ extern "C" int as_conformer_attention(const float* q, const float* k, const floa
     attr = true;
   }
   dim3 grid((T + CA_WARPS - 1) / CA_WARPS, H, B);
-  conformer_attention_kernel<64><<<grid, CA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(conformer_attention_kernel<64>, grid, CA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream), 
+      q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

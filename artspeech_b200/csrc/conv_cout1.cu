@@ -14,6 +14,7 @@ conv_cout1_kernel(const uint16_t* __restrict__ x, long long x_ld, int T, int Cin
                   long long w_tap_stride, int ntaps, int dt0, int dil, const float* __restrict__ bias, const int* __restrict__ lens,
                   float out_scale, int act, float slope, void* y_raw, int y_raw_dtype, long long y_raw_ld,
                   void* y_act, int y_act_dtype, long long y_act_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ __align__(16) uint16_t tile[];        // [(C1_ROWS + halo)][Cin] 16-bit, then weights fp32 [ntaps][Cin]
   const int b = blockIdx.y, t0 = blockIdx.x * C1_ROWS;
   const int halo = (ntaps - 1) * dil;
@@ -78,13 +79,13 @@ int conv_cout1_launch(const as_conv_params* p, cudaStream_t st) {
   dim3 grid((unsigned)((p->T + C1_ROWS - 1) / C1_ROWS), (unsigned)p->B);
   const long long w_tap_stride = (long long)p->CoutP * p->CinP;    // row 0 (the only output channel) of every tap
   if (p->x_dtype == AS_BF16)
-    conv_cout1_kernel<true><<<grid, C1_ROWS, smem, st>>>(reinterpret_cast<const uint16_t*>(p->x), p->x_ld, p->T, p->Cin,
+    ASB_CUDA(launch_k(conv_cout1_kernel<true>, grid, C1_ROWS, smem, st, reinterpret_cast<const uint16_t*>(p->x), p->x_ld, p->T, p->Cin,
         reinterpret_cast<const uint16_t*>(p->w), w_tap_stride, p->ntaps, p->tap_dt[0], dil, p->bias, p->lens, p->out_scale,
-        p->act, p->slope, p->y_raw, p->y_raw_dtype, p->y_raw_ld, p->y_act, p->y_act_dtype, p->y_act_ld);
+        p->act, p->slope, p->y_raw, p->y_raw_dtype, p->y_raw_ld, p->y_act, p->y_act_dtype, p->y_act_ld));
   else
-    conv_cout1_kernel<false><<<grid, C1_ROWS, smem, st>>>(reinterpret_cast<const uint16_t*>(p->x), p->x_ld, p->T, p->Cin,
+    ASB_CUDA(launch_k(conv_cout1_kernel<false>, grid, C1_ROWS, smem, st, reinterpret_cast<const uint16_t*>(p->x), p->x_ld, p->T, p->Cin,
         reinterpret_cast<const uint16_t*>(p->w), w_tap_stride, p->ntaps, p->tap_dt[0], dil, p->bias, p->lens, p->out_scale,
-        p->act, p->slope, p->y_raw, p->y_raw_dtype, p->y_raw_ld, p->y_act, p->y_act_dtype, p->y_act_ld);
+        p->act, p->slope, p->y_raw, p->y_raw_dtype, p->y_raw_ld, p->y_act, p->y_act_dtype, p->y_act_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

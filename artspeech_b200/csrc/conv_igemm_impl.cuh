@@ -437,6 +437,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // barrier init / TMEM alloc / descriptor prefetch above overlap the previous kernel's tail
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
@@ -580,6 +581,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // barrier init / TMEM alloc / descriptor prefetch above overlap the previous kernel's tail
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
@@ -710,6 +712,7 @@ conv_halo_sw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // barrier init / TMEM alloc / descriptor prefetch above overlap the previous kernel's tail
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
@@ -819,7 +822,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const EpiMaps& e
   }
   int grid = num_sms() * ctas_per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_igemm_kernel<BN, BK, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
+  ASB_CUDA(launch_k(conv_igemm_kernel<BN, BK, BF16>, grid, CV_THREADS, smem, st, tmA, tmW, em, a));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -873,7 +876,7 @@ int launch_halo(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeT
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_halo_kernel<BN, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
+  ASB_CUDA(launch_k(conv_halo_kernel<BN, BF16>, grid, CV_THREADS, smem, st, tmA, tmW, em, a));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -930,7 +933,7 @@ int launch_halo_sw(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, Enco
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  conv_halo_sw_kernel<BN, BKC, BF16><<<grid, CV_THREADS, smem, st>>>(tmA, tmW, em, a);
+  ASB_CUDA(launch_k(conv_halo_sw_kernel<BN, BKC, BF16>, grid, CV_THREADS, smem, st, tmA, tmW, em, a));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

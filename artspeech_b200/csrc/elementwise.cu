@@ -29,6 +29,7 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 __global__ void embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table,
                              int n_vocab, int B, int T, int C, float scale,
                              const int* __restrict__ lens, float* out32, void* out16, int dt16) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long row = blockIdx.x;  // b*T + t
   const int b = row / T, t = row % T;
   const bool valid = lens == nullptr || t < lens[b];
@@ -52,6 +53,7 @@ __global__ void layernorm_kernel(const void* __restrict__ x, int xdt, long long 
                                  const float* __restrict__ beta, float eps, int act, float slope,
                                  const int* __restrict__ lens, void* oa, int oadt, long long oa_ld,
                                  void* ob, int obdt, long long ob_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -99,6 +101,7 @@ __global__ void layernorm_kernel(const void* __restrict__ x, int xdt, long long 
 __global__ void instnorm_stats_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T,
                                       int C, const int* __restrict__ lens, float eps,
                                       float* __restrict__ stats) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   __shared__ float red[8][33];
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -142,6 +145,7 @@ __global__ void adain_apply_kernel(const void* __restrict__ x, int xdt, long lon
                                    const int* __restrict__ lens, const float* __restrict__ up_w,
                                    const float* __restrict__ up_b, void* out, int odt,
                                    long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const int To = up_w ? 2 * T : T;
   const long long total = (long long)B * To * C;
   ASB_GRID_STRIDE(i, total, {
@@ -193,6 +197,7 @@ adain_apply_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int 
                        const float* __restrict__ stats, const float* __restrict__ gb, long long gb_ld,
                        float slope, const int* __restrict__ lens, const float* __restrict__ up_w,
                        const float* __restrict__ up_b, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   const int c = (blockIdx.x * 32 + lane) * 4;
@@ -280,6 +285,7 @@ adain_fused_kernel(const void* __restrict__ x, long long x_ld, int T, int TR, in
                    const float* __restrict__ gb, long long gb_ld, float eps, float slope,
                    const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
                    void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ __align__(16) float slab[];            // [TR][32]
   __shared__ float red[8][32];
   __shared__ float part[2][32];                            // this CTA's partial sum / partial squared deviation
@@ -402,6 +408,7 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
                  const float* __restrict__ gb, long long gb_ld, float eps, float slope,
                  const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
                  void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ __align__(128) float slab_raw[];
   __shared__ float red[8][32];
   __shared__ __align__(8) unsigned long long bar_storage;
@@ -501,6 +508,7 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
 __global__ void repeat_rows_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T,
                                    int C, int rep, const int* __restrict__ lens, void* out, int odt,
                                    long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const int To = T * rep;
   const long long total = (long long)B * To * C;
   ASB_GRID_STRIDE(i, total, {
@@ -524,6 +532,7 @@ __global__ void length_regulate_kernel(const void* __restrict__ x, int xdt, long
                                        int C, const int* __restrict__ dur,
                                        const int* __restrict__ lens_t, int rep, int To, void* out,
                                        int odt, long long out_ld, int* __restrict__ out_lens, int vec) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ int cum[];  // [Tt + 1] inclusive prefix sums, cum[0] = 0
   const int b = blockIdx.y;
   const int nt = lens_t ? min(lens_t[b], Tt) : Tt;
@@ -591,6 +600,7 @@ __global__ void conv_small_kernel(const void* __restrict__ x, int xdt, long long
                                   int Cout, const int* __restrict__ lens, void* yr, int yrdt,
                                   long long yr_ld, void* ya, int yadt, long long ya_ld, int act,
                                   float slope) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long total = (long long)B * T * F * Cout;
   ASB_GRID_STRIDE(i, total, {
     const int co = i % Cout;
@@ -620,6 +630,7 @@ conv_small_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B
                       const float* __restrict__ w, const float* __restrict__ bias, int ntaps, SmallTaps taps,
                       int Cout, const int* __restrict__ lens, void* yr, int yrdt, long long yr_ld, void* ya,
                       int yadt, long long ya_ld, int act, float slope, int vec_raw, int vec_act) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ float ws[];   // [ntaps][Cin][Cout] + bias[Cout]
   const int nw = ntaps * Cin * Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) {
@@ -688,6 +699,7 @@ __global__ void dwconv_kernel(const void* __restrict__ x, int xdt, long long x_l
                               int pf, int To, int Fo, const int* __restrict__ lens_in,
                               const int* __restrict__ lens_out, int act, float slope, void* out,
                               int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long total = (long long)B * To * Fo * C;
   ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
@@ -726,6 +738,7 @@ dwconv_time_tiled_kernel(const void* __restrict__ x, int xdt, long long x_ld, in
                          const float* __restrict__ w, const float* __restrict__ bias, int kt, int pt,
                          const int* __restrict__ lens_in, const int* __restrict__ lens_out, int act,
                          float slope, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ float tile[];   // [DWT_ROWS + kt - 1][DWT_CH]
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int b = blockIdx.z, t0 = blockIdx.y * DWT_ROWS, c = blockIdx.x * DWT_CH + tx;
@@ -768,6 +781,7 @@ dwconv_time_tiled_kernel(const void* __restrict__ x, int xdt, long long x_ld, in
 __global__ void avgpool_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T, int F,
                                int C, int pt, int pf, int To, int Fo, void* out, int odt,
                                long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long total = (long long)B * To * Fo * C;
   const float inv = 1.f / (pt * pf);
   ASB_GRID_STRIDE(i, total, {
@@ -795,6 +809,7 @@ __global__ void affine_act_maxpool_kernel(const void* __restrict__ x, int xdt, l
                                           int T, int F, int C, const float* __restrict__ scale,
                                           const float* __restrict__ shift, float slope, int pf, int Fo,
                                           void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long total = (long long)B * T * Fo * C;
   ASB_GRID_STRIDE(i, total, {
     const int c = i % C;
@@ -818,6 +833,7 @@ __global__ void affine_act_maxpool_kernel(const void* __restrict__ x, int xdt, l
 __global__ void global_avgpool_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, int F,
                                       int C, int ts, float slope, void* out, int odt,
                                       long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -839,6 +855,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 
 __global__ void lstm_onestep_kernel(const float* __restrict__ xp, long long xp_ld, long long rows, int H,
                                     void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long total = rows * 2 * H;
   ASB_GRID_STRIDE(i, total, {
     const int j = i % H;
@@ -855,6 +872,7 @@ __global__ void lstm_onestep_kernel(const float* __restrict__ xp, long long xp_l
 // log-norm energy: mel fp32 [B, n_mels, T] -> [B, T]
 // ---------------------------------------------------------------------------------------------
 __global__ void log_norm_kernel(const float* __restrict__ mel, int B, int M, int T, float* out) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * T) return;
   const int t = i % T, b = i / T;
@@ -872,6 +890,7 @@ __global__ void log_norm_kernel(const float* __restrict__ mel, int B, int M, int
 __global__ void transpose_cast_kernel(const void* __restrict__ src, int sdt, void* dst, int ddt, int C,
                                       int T, long long cl_ld, int to_cl, const float* __restrict__ sub,
                                       const float* __restrict__ mul, const int* __restrict__ lens) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -933,7 +952,7 @@ extern "C" int as_embed(const int64_t* tokens, const float* table, int32_t n_voc
   if (B * T == 0) return AS_OK;
   ASB_REQUIRE(tokens && table && (out32 || out16), AS_ERR_SHAPE, "as_embed: null pointer");
   ASB_REQUIRE(!out16 || out16_dtype == AS_F16 || out16_dtype == AS_BF16, AS_ERR_DTYPE, "as_embed: out16 dtype");
-  embed_kernel<<<B * T, 128, 0, ST(stream)>>>(tokens, table, n_vocab, B, T, C, scale, lens, out32, out16, out16_dtype);
+  ASB_CUDA(launch_k(embed_kernel, B * T, 128, 0, ST(stream), tokens, table, n_vocab, B, T, C, scale, lens, out32, out16, out16_dtype));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -948,9 +967,9 @@ extern "C" int as_layernorm(const void* x, int32_t x_dtype, int64_t x_ld, int32_
   ASB_REQUIRE(x && gamma && beta && (out_a || out_b), AS_ERR_SHAPE, "as_layernorm: null pointer");
   ASB_REQUIRE(C > 0 && C <= 32 * LN_MAX_PER_LANE, AS_ERR_SHAPE, "as_layernorm: C=%d unsupported", C);
   ASB_REQUIRE(dt_ok(x_dtype), AS_ERR_DTYPE, "as_layernorm: dtype");
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, rows, T, C, gamma, beta, eps, act,
+  ASB_CUDA(launch_k(layernorm_kernel, cdiv(rows, 8), 256, 0, ST(stream), x, x_dtype, x_ld, rows, T, C, gamma, beta, eps, act,
                                                          slope, lens, out_a, out_a_dtype, out_a_ld, out_b,
-                                                         out_b_dtype, out_b_ld);
+                                                         out_b_dtype, out_b_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -961,7 +980,7 @@ extern "C" int as_instnorm_stats(const void* x, int32_t x_dtype, int64_t x_ld, i
   if (B * C == 0) return AS_OK;
   ASB_REQUIRE(x && stats && dt_ok(x_dtype), AS_ERR_SHAPE, "as_instnorm_stats: bad argument");
   dim3 grid(cdiv(C, 32), B), block(32, 8);
-  instnorm_stats_kernel<<<grid, block, 0, ST(stream)>>>(x, x_dtype, x_ld, T, C, lens, eps, stats);
+  ASB_CUDA(launch_k(instnorm_stats_kernel, grid, block, 0, ST(stream), x, x_dtype, x_ld, T, C, lens, eps, stats));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -982,16 +1001,16 @@ extern "C" int as_adain_apply(const void* x, int32_t x_dtype, int64_t x_ld, int3
     };
     if ((C % 4) == 0 && row_ok(x, x_ld, x_dtype) && row_ok(out, out_ld, out_dtype)) {
       dim3 grid((unsigned)cdiv(C, 128), (unsigned)cdiv(T, AD_ROWS), (unsigned)B);
-      if (up_w) adain_apply_vec_kernel<true><<<grid, 256, 0, ST(stream)>>>(x, x_dtype, x_ld, T, C, stats, gb, gb_ld, slope, lens,
-                                                                           up_w, up_b, out, out_dtype, out_ld);
-      else adain_apply_vec_kernel<false><<<grid, 256, 0, ST(stream)>>>(x, x_dtype, x_ld, T, C, stats, gb, gb_ld, slope, lens,
-                                                                       up_w, up_b, out, out_dtype, out_ld);
+      if (up_w) ASB_CUDA(launch_k(adain_apply_vec_kernel<true>, grid, 256, 0, ST(stream), x, x_dtype, x_ld, T, C, stats, gb, gb_ld, slope, lens,
+                                                                           up_w, up_b, out, out_dtype, out_ld));
+      else ASB_CUDA(launch_k(adain_apply_vec_kernel<false>, grid, 256, 0, ST(stream), x, x_dtype, x_ld, T, C, stats, gb, gb_ld, slope, lens,
+                                                                       up_w, up_b, out, out_dtype, out_ld));
       ASB_CUDA(cudaGetLastError());
       return AS_OK;
     }
   }
-  adain_apply_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, C, stats, gb, gb_ld, slope,
-                                                            lens, up_w, up_b, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(adain_apply_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, C, stats, gb, gb_ld, slope,
+                                                            lens, up_w, up_b, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1031,10 +1050,10 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
           attr = true;
         }
         dim3 grid(cdiv(C, 32), (unsigned)B);
-        if (up_w) adain_tma_kernel<true><<<grid, 256, smem, ST(stream)>>>(tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
-                                                                         out, out_dtype, out_ld, stats);
-        else adain_tma_kernel<false><<<grid, 256, smem, ST(stream)>>>(tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
-                                                                     out, out_dtype, out_ld, stats);
+        if (up_w) ASB_CUDA(launch_k(adain_tma_kernel<true>, grid, 256, smem, ST(stream), tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
+                                                                         out, out_dtype, out_ld, stats));
+        else ASB_CUDA(launch_k(adain_tma_kernel<false>, grid, 256, smem, ST(stream), tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
+                                                                     out, out_dtype, out_ld, stats));
         ASB_CUDA(cudaGetLastError());
         return AS_OK;
       }
@@ -1053,8 +1072,8 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
                                     ADF_MAX_TR * 32 * 4));                                                      \
       attr = true;                                                                                             \
     }                                                                                                          \
-    adain_fused_kernel<UP_, XDT_><<<grid, 256, smem, ST(stream)>>>(x, x_ld, T, TR, C, gb, gb_ld, eps, slope, lens, up_w, \
-                                                                   up_b, out, out_dtype, out_ld, stats);       \
+    ASB_CUDA(launch_k(adain_fused_kernel<UP_, XDT_>, grid, 256, smem, ST(stream), x, x_ld, T, TR, C, gb, gb_ld, eps, slope, lens, up_w, \
+                                                                   up_b, out, out_dtype, out_ld, stats));       \
   } while (0)
     if (up_w) {
       if (x_dtype == AS_F32) ADF_LAUNCH(true, AS_F32); else if (x_dtype == AS_F16) ADF_LAUNCH(true, AS_F16); else ADF_LAUNCH(true, AS_BF16);
@@ -1077,7 +1096,7 @@ extern "C" int as_repeat_rows(const void* x, int32_t x_dtype, int64_t x_ld, int3
   const long long total = (long long)B * T * rep * C;
   if (total == 0) return AS_OK;
   ASB_REQUIRE(x && out && rep >= 1, AS_ERR_SHAPE, "as_repeat_rows: bad argument");
-  repeat_rows_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, C, rep, lens, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(repeat_rows_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, C, rep, lens, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1099,8 +1118,8 @@ extern "C" int as_length_regulate(const void* x, int32_t x_dtype, int64_t x_ld, 
     else if (x_dtype == AS_F32 && out_dtype != AS_F32 && C % 8 == 0) vec = 2;
   }
   dim3 grid((unsigned)((To + LR_ROWS - 1) / LR_ROWS > 0 ? (To + LR_ROWS - 1) / LR_ROWS : 1), (unsigned)B);
-  length_regulate_kernel<<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, Tt, C, dur, lens_t, rep, To, out,
-                                                         out_dtype, out_ld, out_lens, vec);
+  ASB_CUDA(launch_k(length_regulate_kernel, grid, 256, smem, ST(stream), x, x_dtype, x_ld, Tt, C, dur, lens_t, rep, To, out,
+                                                         out_dtype, out_ld, out_lens, vec));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1123,15 +1142,15 @@ extern "C" int as_conv_small(const void* x, int32_t x_dtype, int64_t x_ld, int32
     auto al16 = [](const void* ptr, long long ld, int dt) {
       return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld * (dt == AS_F32 ? 4 : 2)) & 15) == 0;
     };
-    conv_small_vec_kernel<<<ew_grid(total / 8), 256, wsmem, ST(stream)>>>(
+    ASB_CUDA(launch_k(conv_small_vec_kernel, ew_grid(total / 8), 256, wsmem, ST(stream), 
         x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps, Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
-        y_act_dtype, y_act_ld, act, slope, al16(y_raw, y_raw_ld, y_raw_dtype) ? 1 : 0, al16(y_act, y_act_ld, y_act_dtype) ? 1 : 0);
+        y_act_dtype, y_act_ld, act, slope, al16(y_raw, y_raw_ld, y_raw_dtype) ? 1 : 0, al16(y_act, y_act_ld, y_act_dtype) ? 1 : 0));
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
-  conv_small_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps,
+  ASB_CUDA(launch_k(conv_small_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps,
                                                            Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
-                                                           y_act_dtype, y_act_ld, act, slope);
+                                                           y_act_dtype, y_act_ld, act, slope));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1147,14 +1166,14 @@ extern "C" int as_dwconv(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B
   if (F == 1 && Fo == 1 && kf == 1 && sf == 1 && st == 1 && pf == 0 && To == T && kt <= DWT_MAXK && kt >= 5) {
     dim3 grid(cdiv(C, DWT_CH), cdiv(T, DWT_ROWS), (unsigned)B);
     const size_t smem = (size_t)(DWT_ROWS + kt - 1) * DWT_CH * sizeof(float);
-    dwconv_time_tiled_kernel<<<grid, 256, smem, ST(stream)>>>(x, x_dtype, x_ld, T, C, glu, w, bias, kt, pt, lens_in, lens_out,
-                                                            act, slope, out, out_dtype, out_ld);
+    ASB_CUDA(launch_k(dwconv_time_tiled_kernel, grid, 256, smem, ST(stream), x, x_dtype, x_ld, T, C, glu, w, bias, kt, pt, lens_in, lens_out,
+                                                            act, slope, out, out_dtype, out_ld));
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
-  dwconv_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, F, C, glu, w, bias, kt, kf, st, sf,
+  ASB_CUDA(launch_k(dwconv_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, glu, w, bias, kt, kf, st, sf,
                                                        pt, pf, To, Fo, lens_in, lens_out, act, slope, out,
-                                                       out_dtype, out_ld);
+                                                       out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1166,7 +1185,7 @@ extern "C" int as_avgpool(const void* x, int32_t x_dtype, int64_t x_ld, int32_t 
   const int To = (T + pt - 1) / pt, Fo = F / pf;
   const long long total = (long long)B * To * Fo * C;
   if (total == 0) return AS_OK;
-  avgpool_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, F, C, pt, pf, To, Fo, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(avgpool_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, pt, pf, To, Fo, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1179,8 +1198,8 @@ extern "C" int as_affine_act_maxpool(const void* x, int32_t x_dtype, int64_t x_l
   const int Fo = F / pf;
   const long long total = (long long)B * T * Fo * C;
   if (total == 0) return AS_OK;
-  affine_act_maxpool_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, x_dtype, x_ld, B, T, F, C, scale, shift,
-                                                                   slope, pf, Fo, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(affine_act_maxpool_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, scale, shift,
+                                                                   slope, pf, Fo, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1191,7 +1210,7 @@ extern "C" int as_global_avgpool(const void* x, int32_t x_dtype, int64_t x_ld, i
   ASB_REQUIRE(x && out && t_stride >= 1 && T >= 1 && F >= 1, AS_ERR_SHAPE, "as_global_avgpool: bad argument");
   if (B * C == 0) return AS_OK;
   dim3 grid(cdiv(C, 128), B);
-  global_avgpool_kernel<<<grid, 128, 0, ST(stream)>>>(x, x_dtype, x_ld, T, F, C, t_stride, slope, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(global_avgpool_kernel, grid, 128, 0, ST(stream), x, x_dtype, x_ld, T, F, C, t_stride, slope, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1201,7 +1220,7 @@ extern "C" int as_lstm_onestep(const float* xproj, int64_t xproj_ld, int64_t row
   const long long total = rows * 2 * H;
   if (total == 0) return AS_OK;
   ASB_REQUIRE(xproj && out, AS_ERR_SHAPE, "as_lstm_onestep: null pointer");
-  lstm_onestep_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(xproj, xproj_ld, rows, H, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(lstm_onestep_kernel, ew_grid(total), 256, 0, ST(stream), xproj, xproj_ld, rows, H, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1209,7 +1228,7 @@ extern "C" int as_lstm_onestep(const float* xproj, int64_t xproj_ld, int64_t row
 extern "C" int as_log_norm(const float* mel, int32_t B, int32_t n_mels, int32_t T, float* out, void* stream) {
   if (B * T == 0) return AS_OK;
   ASB_REQUIRE(mel && out, AS_ERR_SHAPE, "as_log_norm: null pointer");
-  log_norm_kernel<<<cdiv((long long)B * T, 128), 128, 0, ST(stream)>>>(mel, B, n_mels, T, out);
+  ASB_CUDA(launch_k(log_norm_kernel, cdiv((long long)B * T, 128), 128, 0, ST(stream), mel, B, n_mels, T, out));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -1222,8 +1241,8 @@ extern "C" int as_transpose_cast(const void* src, int32_t src_dtype, void* dst, 
   ASB_REQUIRE(src && dst && dt_ok(src_dtype) && dt_ok(dst_dtype), AS_ERR_SHAPE, "as_transpose_cast: bad argument");
   ASB_REQUIRE((sub == nullptr) == (mul == nullptr), AS_ERR_SHAPE, "as_transpose_cast: sub/mul must come together");
   dim3 grid(cdiv(T, 32), cdiv(C, 32), B), block(32, 8);
-  transpose_cast_kernel<<<grid, block, 0, ST(stream)>>>(src, src_dtype, dst, dst_dtype, C, T, cl_ld,
-                                                       to_channels_last, sub, mul, lens);
+  ASB_CUDA(launch_k(transpose_cast_kernel, grid, block, 0, ST(stream), src, src_dtype, dst, dst_dtype, C, T, cl_ld,
+                                                       to_channels_last, sub, mul, lens));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

@@ -28,6 +28,7 @@ template <int BG>
 __global__ void __launch_bounds__(1024, 1) bilstm_kernel(const float* __restrict__ xproj, long long xp_ld,
                               const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T, int H,
                               const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ float sm[];
   const int G = 4 * H;
   float* hbuf = sm;                 // [2][BG][H] ping-pong
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256, 1)
 bilstm128_mma_kernel(const float* __restrict__ xproj, long long xp_ld,
                      const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T,
                      const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   constexpr int H = L128_H, G = 4 * H;
   __shared__ __align__(16) __half hs[2][L128_NB][L128_HP];
   __shared__ int s_len[L128_NB];
@@ -288,6 +290,7 @@ __global__ void __cluster_dims__(L256_NC, 1, 1) __launch_bounds__(256, 1)
 bilstm256_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
                          const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T,
                          const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   constexpr int H = L256_H, G = 4 * H;
   __shared__ __align__(16) __half hs[2][L256_NB][L256_HP];
   __shared__ int s_len[L256_NB];
@@ -421,23 +424,23 @@ extern "C" int as_bilstm(const float* xproj, int64_t xproj_ld, const float* whh,
   ASB_REQUIRE(H == 128 || H == 256 || H == 64, AS_ERR_SHAPE, "as_bilstm: hidden size %d unsupported (64, 128 or 256)", H);
   if (H == 128) {
     dim3 grid128((B + L128_NB - 1) / L128_NB, 2);
-    bilstm128_mma_kernel<<<grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld);
+    ASB_CUDA(launch_k(bilstm128_mma_kernel, grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
+        xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
   if (H == 256) {
     dim3 grid256(L256_NC * ((B + L256_NB - 1) / L256_NB), 2);
-    bilstm256_cluster_kernel<<<grid256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld);
+    ASB_CUDA(launch_k(bilstm256_cluster_kernel, grid256, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
+        xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
   const int G = 4 * H;
   const size_t smem = sizeof(float) * ((size_t)2 * LSTM_BG * H + (size_t)LSTM_BG * G);
   dim3 grid((B + LSTM_BG - 1) / LSTM_BG, 2);
-  bilstm_kernel<LSTM_BG><<<grid, G, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      xproj, xproj_ld, whh, B, T, H, lens, out, out_dtype, out_ld);
+  ASB_CUDA(launch_k(bilstm_kernel<LSTM_BG>, grid, G, smem, reinterpret_cast<cudaStream_t>(stream), 
+      xproj, xproj_ld, whh, B, T, H, lens, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256)
 mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
            const int32_t* __restrict__ y_len, float* __restrict__ path, int Tx, int Ty,
            int tie_move, uint32_t* __restrict__ dir_ws, int dir_in_smem, int cw, int NW) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   constexpr int WR = 32 * R;       // rows per warp
   constexpr int PX = WR + 1;       // odd pitch of a warp's transposed [col][row] sub-tile
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -257,8 +258,8 @@ template <int R>
 static int launch_mas(const MasPlan& p, const float* value, const int32_t* x_len, const int32_t* y_len,
                       float* path, int B, int Tx, int Ty, int tie_mode, void* ws, cudaStream_t st) {
   ASB_CUDA(cudaFuncSetAttribute(mas_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  mas_kernel<R><<<B, 32 * p.NW, p.smem, st>>>(value, x_len, y_len, path, Tx, Ty, tie_mode,
-                                              reinterpret_cast<uint32_t*>(ws), p.dir_in_smem, p.cw, p.NW);
+  ASB_CUDA(launch_k(mas_kernel<R>, B, 32 * p.NW, p.smem, st, value, x_len, y_len, path, Tx, Ty, tie_mode,
+                                              reinterpret_cast<uint32_t*>(ws), p.dir_in_smem, p.cw, p.NW));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

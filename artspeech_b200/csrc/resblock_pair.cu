@@ -148,6 +148,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // barrier init / TMEM alloc / descriptor prefetch above overlap the previous kernel's tail
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   // TMEM columns: D1[buf][mtile] at (buf*2 + mtile)*C, D2[buf][mtile] at (2*ND + buf*2 + mtile)*C
@@ -464,7 +465,7 @@ static int launch_pair(const PairMaps& maps, const PairArgs& a, size_t smem, cud
   }
   int grid = num_sms();
   if (grid > a.total_tiles) grid = a.total_tiles;
-  resblock_pair_kernel<C, BF16><<<grid, RP_THREADS, smem, st>>>(maps, a);
+  ASB_CUDA(launch_k(resblock_pair_kernel<C, BF16>, grid, RP_THREADS, smem, st, maps, a));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }

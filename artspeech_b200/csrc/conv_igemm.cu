@@ -118,7 +118,19 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
               "as_conv_igemm: ntaps=%d out of range [1,%d]", p->ntaps, CV_MAX_TAPS);
   ASB_REQUIRE(p->x && p->w && p->tap_dt && p->tap_df, AS_ERR_SHAPE, "as_conv_igemm: null pointer");
   const int bk = p->Cin >= 64 ? 64 : 32;
-  const int bn = pick_tile_n(p->Cout);
+  int bn = pick_tile_n(p->Cout);
+  {
+    // small problems: with 128 x 256 tiles a GEMM of a few thousand rows fills a fraction of the SMs and
+    // every CTA streams the whole weight matrix; 128 x 128 tiles double the CTAs and halve the bytes each
+    // one pulls from L2 (two CTAs per SM).  Only when the packed width allows it (CoutP % 128 == 0).
+    static const int small_tiles = getenv("ASB_BN128_MAX_TILES") ? atoi(getenv("ASB_BN128_MAX_TILES")) : 74;
+    if (bn == 256 && p->CoutP % 128 == 0) {
+      int tF0 = 1;
+      while (tF0 < 128 && (p->Fo % (tF0 * 2)) == 0) tF0 <<= 1;
+      const long long m_tiles0 = (long long)p->B * ((p->To + 128 / tF0 - 1) / (128 / tF0)) * ((p->Fo + tF0 - 1) / tF0);
+      if (m_tiles0 * (p->CoutP / 256) <= small_tiles) bn = 128;
+    }
+  }
   ASB_REQUIRE(p->CinP % bk == 0 && p->CinP >= p->Cin, AS_ERR_SHAPE,
               "as_conv_igemm: CinP=%d must be a multiple of %d and >= Cin=%d", p->CinP, bk, p->Cin);
   ASB_REQUIRE(p->CoutP % bn == 0 && p->CoutP >= p->Cout, AS_ERR_SHAPE,

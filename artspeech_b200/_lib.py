@@ -123,5 +123,6 @@ SIGNATURES.update({
     "as_bilstm": (C.c_int, [_V, _L, _V, _I, _I, _I, _V, _V, _I, _L, _V]),
     "as_lstm_onestep": (C.c_int, [_V, _L, _L, _I, _V, _I, _L, _V]),
     "as_log_norm": (C.c_int, [_V, _I, _I, _I, _V, _V]),
+    "as_log_mel": (C.c_int, [_V, _L, _V, _I, _I, _V, _V, _V, _V, _I, _I, _I, _F, _F, _F, _V, _I, _V]),
     "as_transpose_cast": (C.c_int, [_V, _I, _V, _I, _I, _I, _I, _L, _I, _V, _V, _V, _V]),
 })

@@ -334,6 +334,24 @@ def run_ours(args):
                     "bytes_per_launch": ad_bytes, "l2": "6 rotating input sets (474 MB), graph replay"}
         del xs, keep
 
+    # the step before the path: log-mel front-end of the 16 reference recordings (3 s each)
+    fe_info = None
+    if rank == 0:
+        from artspeech_b200 import frontend
+        fe = frontend.LogMel().to(dev)
+        wv = torch.randn(B_PER_GPU, TR * 300, device=dev) * 0.1
+        for _ in range(3):
+            fe(wv)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(20):
+            fe(wv)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        fe_info = {"kernel": "log_mel_kernel (STFT 2048/1200/300 + 80 mel + log, fp32)", "recordings": B_PER_GPU,
+                   "seconds_each": TR * 300 / 24000.0, "us": e0.elapsed_time(e1) / 20 * 1e3,
+                   "note": "not part of the timed step (reference mels are the step's inputs, as in BASELINE configs)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -366,6 +384,7 @@ def run_ours(args):
                      "flops_per_step": voc_flops, "vocoder_ms": voc_ms,
                      "vocoder_share_of_step": voc_ms / (ms / args.steps)},
         "roofline_hbm": hbm_info,
+        "frontend": fe_info,
         "mas": mas_info,
     }
     if world == 1 and not args.no_cpu_baseline:

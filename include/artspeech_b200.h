@@ -297,6 +297,21 @@ int as_transpose_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst
                       int32_t C, int32_t T, int64_t cl_ld, int32_t to_channels_last,
                       const float* sub, const float* mul, const int32_t* lens, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Log-mel front-end of the reference recordings — replaces test.py:40-47 / meldataset.py:42-49:
+ * torchaudio MelSpectrogram(n_mels, n_fft 2048, win_length, hop) (centre = True, reflect padding, periodic
+ * Hann window zero-padded to n_fft, power 2, HTK filterbank) then (log(log_eps + mel) - mean) / std.
+ *   wave   fp32 [B, N] rows of wave_ld samples; lens int32 [B] samples per recording or NULL (each must
+ *          exceed n_fft / 2); window fp32 [n_fft]; twiddle fp32 [n_fft/2][2] = (cos, -sin)(2 pi k / n_fft);
+ *   fb     fp32 [n_fft/2 + 1, n_mels]; fb_range int32 [n_mels][2] = first bin and bin count of each filter;
+ *   out    fp32 [B, n_mels, n_frames] (channels-first like the reference's mel), n_frames = 1 + N / hop;
+ *          frames beyond 1 + lens[b] / hop are written as zeros.
+ * ------------------------------------------------------------------------------------------ */
+int as_log_mel(const float* wave, int64_t wave_ld, const int32_t* lens, int32_t B, int32_t N,
+               const float* window, const float* twiddle, const float* fb, const int32_t* fb_range,
+               int32_t n_fft, int32_t hop, int32_t n_mels, float log_eps, float mean, float std,
+               float* out, int32_t n_frames, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

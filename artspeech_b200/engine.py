@@ -43,29 +43,39 @@ class Synthesizer:
         self.launches_per_call = None
 
     # ---------------------------------------------------------------------------------------
-    def _forward(self, tokens, tok_lens, mels, mel_lens, durations, host_meta=None):
+    @torch.no_grad()
+    def encode_voice(self, mels, mel_lens):
+        """Style-encoder pass for a batch of reference recordings: ``mels`` fp32 [B,80,Tr] (device), ``mel_lens``
+        int64 [B] (host) -> ``(f0, n, ema, Style)``, reusable as ``synthesize(..., voice=...)`` for every
+        utterance spoken with these voices (item i of the batch uses voice i)."""
+        ml = [int(v) for v in mel_lens.tolist()]
+        return tuple(self.model.style_encoder(mels, mel_lens.to(self.device), "second", self.model.distribution,
+                                              host_lengths=ml))
+
+    def _forward(self, tokens, tok_lens, mels, mel_lens, durations, host_meta=None, voice=None):
         mel, aux = self.model([tokens, tok_lens, mels, mel_lens], step="test", durations=durations, return_aux=True,
-                              host_meta=host_meta)
+                              host_meta=host_meta, voice=voice)
         wav = self.generator(mel, aux["mel_lengths"])
         return wav.view(wav.shape[0], -1), aux["mel_lengths"], mel
 
     @torch.no_grad()
-    def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None):
+    def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None, voice=None):
         """``tokens`` int64 [B,Tt] (device), ``tok_lens`` / ``mel_lens`` int64 [B] (HOST tensors keep the
         pass sync-free), ``mels`` fp32 [B,80,Tr] (device), ``durations`` int64 [B,Tt] (HOST) or None
-        (use the duration predictor; costs one device->host sync).
+        (use the duration predictor; costs one device->host sync).  ``voice``: cached ``encode_voice`` result
+        (the style encoder is then skipped).
         Returns (wav fp32 [B, 300*Tm_max], mel_lengths int32 [B] (device), mel fp32 [B,80,Tm_max])."""
         self.last_stream = torch.cuda.current_stream(self.device)
         host_side = durations is not None and not durations.is_cuda and not tok_lens.is_cuda and not mel_lens.is_cuda
         if not host_side:
-            return self._forward(tokens, tok_lens, mels, mel_lens, durations)
+            return self._forward(tokens, tok_lens, mels, mel_lens, durations, voice=voice)
         tl, ml = [int(v) for v in tok_lens.tolist()], [int(v) for v in mel_lens.tolist()]
         Lmax = max(int(durations[b, :tl[b]].sum()) for b in range(len(tl)))
         meta = {"mel_lens": ml, "Lmax": Lmax}
         graphable = self.use_cuda_graph and all(v == mels.shape[2] for v in ml)
         if not graphable:
             return self._forward(tokens, tok_lens.to(self.device), mels, mel_lens.to(self.device),
-                                 durations.to(self.device), meta)
+                                 durations.to(self.device), meta, voice=voice)
         slot = 0
         cur = torch.cuda.current_stream(self.device)
         run_stream = cur
@@ -75,11 +85,13 @@ class Synthesizer:
             slot = self._calls % self.pipeline_depth
             run_stream = self._slot_streams[slot]
         self._calls += 1
-        key = (slot, tuple(tokens.shape), tuple(mels.shape), tuple(tl), tuple(ml), hash(durations.numpy().tobytes()))
+        key = (slot, voice is not None, tuple(tokens.shape), tuple(mels.shape), tuple(tl), tuple(ml),
+               hash(durations.numpy().tobytes()))
         entry = self._graphs.get(key)
         if entry is None:
             static_tok = tokens.clone()
             static_mel = mels.clone()
+            static_voice = None if voice is None else tuple(v.clone() for v in voice)
             tok_lens, mel_lens = tok_lens.to(self.device), mel_lens.to(self.device)
             durations = durations.to(self.device)
             # warm-up on a side stream (weight packing, cudaFuncSetAttribute, allocator)
@@ -87,18 +99,18 @@ class Synthesizer:
             s.wait_stream(cur)
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta)
+                    self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta, voice=static_voice)
             cur.wait_stream(s)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             before = ops.launch_count
             with torch.cuda.graph(g):
-                out = self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta)
+                out = self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta, voice=static_voice)
             self.launches_per_call = ops.launch_count - before
             # the captured kernels read these device tensors on every replay: keep them alive with the graph
-            entry = (g, static_tok, static_mel, out, (tok_lens, mel_lens, durations))
+            entry = (g, static_tok, static_mel, out, (tok_lens, mel_lens, durations), static_voice)
             self._graphs[key] = entry
-        g, static_tok, static_mel, out, _keepalive = entry
+        g, static_tok, static_mel, out, _keepalive, static_voice = entry
         if run_stream is not cur:
             # the slot's stream picks up after whatever produced the inputs on the caller's stream;
             # the caller's stream never waits for the slot (that would serialise the pipeline)
@@ -107,9 +119,15 @@ class Synthesizer:
             run_stream.wait_event(ready)
             tokens.record_stream(run_stream)
             mels.record_stream(run_stream)
+            for v in (voice or ()):
+                v.record_stream(run_stream)
         with torch.cuda.stream(run_stream):
             static_tok.copy_(tokens, non_blocking=True)
-            static_mel.copy_(mels, non_blocking=True)
+            if static_voice is None:
+                static_mel.copy_(mels, non_blocking=True)
+            else:
+                for dst, src in zip(static_voice, voice):
+                    dst.copy_(src, non_blocking=True)
             g.replay()
             if run_stream is not cur:
                 done = torch.cuda.Event()

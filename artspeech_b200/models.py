@@ -527,10 +527,13 @@ class ArtsSpeech(nn.Module):
 
     @torch.no_grad()
     def forward(self, batch, s2s_attn=None, s2s_attn_mono=None, step="test", mode="train", epoch=0,
-                durations: Optional[torch.Tensor] = None, return_aux: bool = False, host_meta: Optional[dict] = None):
+                durations: Optional[torch.Tensor] = None, return_aux: bool = False, host_meta: Optional[dict] = None,
+                voice: Optional[tuple] = None):
         """``host_meta`` (optional, keeps the pass free of device->host syncs so it can be captured in
         a CUDA graph): ``{"mel_lens": [int], "Lmax": int}`` = reference-mel lengths and the largest
-        ``sum(durations[b, :len_b])``; requires ``durations``."""
+        ``sum(durations[b, :len_b])``; requires ``durations``.
+        ``voice`` (optional): ``(f0, n, ema, Style)`` as returned by the style encoder for these utterances'
+        reference recordings; skips the style encoder (``mels`` is then only used for its shape)."""
         if step != "test":
             raise NotImplementedError("artspeech_b200 accelerates the synthesis path (step='test'); the "
                                       "training branches (models.py:291-354) stay with the reference")
@@ -544,11 +547,18 @@ class ArtsSpeech(nn.Module):
         hm = host_meta or {}
         # the two text encoders and the style encoder are independent (:357-359): run them on
         # concurrent streams (each is a latency-bound chain of small kernels)
-        T_en, A_en, (f0_ext, n_ext, ema_ext, style) = ops.run_concurrently([
-            lambda: self.text_encoder(texts, input_lengths),                             # [B,Tt,512] fp32 (:357)
-            lambda: self.arts_encoder(texts, input_lengths),                             # (:358)
-            lambda: self.style_encoder(mels, mel_input_length, "second", self.distribution,
-                                       host_lengths=hm.get("mel_lens"))], dev)           # (:359)
+        if voice is not None:
+            # style-encoder outputs of the reference voice computed earlier (engine.Synthesizer.encode_voice):
+            # the 30 GFLOP style encoder runs once per voice instead of once per utterance
+            f0_ext, n_ext, ema_ext, style = voice
+            T_en, A_en = ops.run_concurrently([lambda: self.text_encoder(texts, input_lengths),
+                                               lambda: self.arts_encoder(texts, input_lengths)], dev)
+        else:
+            T_en, A_en, (f0_ext, n_ext, ema_ext, style) = ops.run_concurrently([
+                lambda: self.text_encoder(texts, input_lengths),                             # [B,Tt,512] fp32 (:357)
+                lambda: self.arts_encoder(texts, input_lengths),                             # (:358)
+                lambda: self.style_encoder(mels, mel_input_length, "second", self.distribution,
+                                           host_lengths=hm.get("mel_lens"))], dev)           # (:359)
         if durations is None:
             duration = self.durationPredictor(texts, ema_ext, input_lengths, mel_input_length,
                                               host_mel_lengths=hm.get("mel_lens"))                # (:360)

@@ -245,6 +245,16 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
 
+    # extra (not the headline): the same step with the style-encoder outputs cached per reference voice
+    # (engine.encode_voice) — the serving case where many utterances share a voice
+    voice = syn.encode_voice(mel_d, mel_lens)
+
+    def step_voice_cached():
+        return syn.synthesize(tok_d, tok_lens, mel_d, mel_lens, dur, voice=voice)
+    for _ in range(3):
+        step_voice_cached()
+    ms_cached = timed(step_voice_cached, args.steps)
+
     # dominant kernel family: the vocoder's tensor-core convolutions (27 fused resblock-pair launches + 24
     # implicit-GEMM launches, nothing else).
     # Timed alone, replayed from a CUDA graph (no launch gaps), with CUDA events on the launch stream.
@@ -385,6 +395,9 @@ def run_ours(args):
                      "vocoder_share_of_step": voc_ms / (ms / args.steps)},
         "roofline_hbm": hbm_info,
         "frontend": fe_info,
+        "voice_cached": {"value": world * B_PER_GPU * AUDIO_S_PER_UTT * args.steps / (ms_cached / 1e3), "unit": "audio-s/s",
+                         "ms_per_step": ms_cached / args.steps,
+                         "note": "style-encoder outputs cached per reference voice (not the BASELINE config: informational)"},
         "mas": mas_info,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -180,3 +180,25 @@ def test_pipelined_engine_matches_serial(model_gpu):
     torch.cuda.synchronize()
     for step, (h, w) in enumerate(zip(hosts, want)):
         assert torch.equal(h, w), f"step {step}: pipelined output differs"
+
+
+def test_voice_cache_matches_full_pass(model_gpu):
+    """engine.Synthesizer.encode_voice + synthesize(voice=...) (style encoder once per voice)
+    gives exactly the waveforms of the full pass, eagerly and through the CUDA-graph path."""
+    from artspeech_b200 import engine
+    model, g = model_gpu
+    gen = util.generator(0).to(DEV)
+    B, Tt, Tr = 2, 30, 100
+    gsrc = torch.Generator().manual_seed(9)
+    tok = torch.randint(1, 178, (B, Tt), generator=gsrc).to(DEV)
+    mel = (torch.randn(B, 80, Tr, generator=gsrc) * 0.5).to(DEV)
+    tl, ml = torch.full((B,), Tt), torch.full((B,), Tr)
+    dur = torch.randint(1, 4, (B, Tt), generator=gsrc)
+    for use_graph in (False, True):
+        syn = engine.Synthesizer(model, gen, device=DEV, use_cuda_graph=use_graph)
+        full, _, mel_full = syn.synthesize(tok, tl, mel, ml, dur)
+        full, mel_full = full.clone(), mel_full.clone()
+        voice = syn.encode_voice(mel, ml)
+        for _ in range(2):
+            cached, _, mel_cached = syn.synthesize(tok, tl, mel, ml, dur, voice=voice)
+        assert torch.equal(mel_cached, mel_full) and torch.equal(cached, full), f"graph={use_graph}"

@@ -26,6 +26,8 @@ bool conv_cout1_eligible(const as_conv_params* p);
 int conv_cout1_launch(const as_conv_params* p, cudaStream_t st);
 
 // instantiated in conv_inst_*.cu
+extern template int launch_conv_2cta<64, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, cudaStream_t);
+extern template int launch_conv_2cta<64, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, cudaStream_t);
 extern template int launch_conv<16, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
 extern template int launch_conv<16, 32, false>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
 extern template int launch_conv<32, 32, true>(const CUtensorMap&, const CUtensorMap&, const EpiMaps&, ConvArgs&, int, cudaStream_t);
@@ -270,6 +272,22 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
 #define HALO_CASE(BN_) if (bn == BN_) return bf ? launch_halo<BN_, true>(p, a, em, enc, st) : launch_halo<BN_, false>(p, a, em, enc, st);
     HALO_CASE(16) HALO_CASE(32) HALO_CASE(64)
 #undef HALO_CASE
+  }
+  {
+    // 256-wide tiles with at least one full pair of M-tiles: CTA pairs share the weight tile (cta_group::2)
+    static const bool no_2cta = getenv("ASB_NO_2CTA") != nullptr;
+    const int m_tiles_all = p->B * a.n_ttiles * a.n_ftiles;
+    if (!no_2cta && bn == 256 && bk == 64 && m_tiles_all >= 2) {
+      CUtensorMap tmWh;
+      cuuint64_t dims[2] = {(cuuint64_t)p->CinP, (cuuint64_t)p->ntaps * p->CoutP};
+      cuuint64_t strides[1] = {(cuuint64_t)p->CinP * 2};
+      cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(bn / 2)};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(&tmWh, dt, 2, const_cast<void*>(p->w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(W half) failed: %d", (int)r);
+      return p->x_dtype == AS_BF16 ? launch_conv_2cta<64, true>(tmA, tmWh, em, a, st) : launch_conv_2cta<64, false>(tmA, tmWh, em, a, st);
+    }
   }
   const int total_tiles = p->B * a.n_ttiles * a.n_ftiles * (p->CoutP / bn);
 #define CV_CASE(BN_, BK_)                                                                    \

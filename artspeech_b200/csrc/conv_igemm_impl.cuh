@@ -150,7 +150,12 @@ __device__ __forceinline__ void store_fast(char* p, int kind, const float (&v)[1
 template <int BN, bool BF16>
 __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint32_t tfull0,
                                              uint32_t tempty0, int warp, int lane, int m_tiles,
-                                             int total_tiles, const float* bias_s) {
+                                             int total_tiles, const float* bias_s, int tile_first = -1,
+                                             int tile_step = 0, int cl = 1, int rank = 0, bool remote_tempty = false) {
+  // 2-CTA kernels: `tile` counts cluster-level super-tiles (cl adjacent M-tiles x one N-tile), m_tiles is
+  // the number of M units (pairs), this CTA takes M-tile unit*cl + rank; tempty0 is then the leader's
+  // barrier as a shared::cluster address.
+  if (tile_first < 0) { tile_first = blockIdx.x; tile_step = gridDim.x; }
   // 16-bit residual rows are fetched into registers BEFORE the accumulator wait (ncu: the epilogue
   // warps were stalled on these loads, long_scoreboard ~12 cycles/issue): up to 128 channels/row.
   // BN = 256 runs one CTA per SM (<= 204 regs/thread): 128 channels; narrower tiles run two CTAs
@@ -163,15 +168,15 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
   const int m = q * 32 + lane;     // tile row
   const int it_ = m / a.tF, if_ = m - it_ * a.tF;
   int lt = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+  for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++lt) {
     if ((lt & 1) != wg) continue;
-    int mt = tile % m_tiles;
+    int mt = (tile % m_tiles) * cl + rank;
     const int n0 = (tile / m_tiles) * BN;
     const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
     const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
     const int b = mt;
     const int t = tt * a.tT + it_, f = ft * a.tF + if_;
-    const bool row_ok = (t < a.To) && (f < a.Fo);
+    const bool row_ok = (t < a.To) && (f < a.Fo) && (b < a.B);   // b == B: the padding tile of an odd pair
     bool masked = false;
     if (a.lens != nullptr && row_ok) masked = t >= __ldg(a.lens + b);
     const long long row = ((long long)b * a.To + t) * a.Fo + f;
@@ -262,7 +267,10 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     // all TMEM reads of this stage are complete (tcgen05.wait::ld above): hand it back to the MMA warp
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
+    if (lane == 0) {
+      if (remote_tempty) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(wg)) : "memory");
+    }
   }
 }
 
@@ -278,7 +286,10 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
 template <int BN, bool BF16>
 __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMaps& maps, uint32_t tmem_base,
                                                  uint32_t tfull0, uint32_t tempty0, int warp, int lane, int m_tiles,
-                                                 int total_tiles, const float* bias_s, uint32_t epi_base) {
+                                                 int total_tiles, const float* bias_s, uint32_t epi_base,
+                                                 int tile_first = -1, int tile_step = 0, int cl = 1, int rank = 0,
+                                                 bool remote_tempty = false) {
+  if (tile_first < 0) { tile_first = blockIdx.x; tile_step = gridDim.x; }
   const int ew = warp - 2;                 // 0..7
   const int wg = ew >> 2;
   const int q = warp & 3;
@@ -295,14 +306,14 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
   const uint32_t sw = (EPC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
   uint32_t rphase = 0;
   int lt = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+  for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++lt) {
     if ((lt & 1) != wg) continue;
-    const int mt = tile % m_tiles;
+    const int mt = (tile % m_tiles) * cl + rank;
     const int n0 = (tile / m_tiles) * BN;
-    const int tt = mt % a.n_ttiles, b = mt / a.n_ttiles;
+    const int tt = mt % a.n_ttiles, b = mt / a.n_ttiles;      // b == B (padding tile of an odd pair): TMA clips everything
     const int t_base = tt * 128 + q * 32;
     const int t = t_base + lane;
-    const bool masked = (a.lens != nullptr) && (t < a.To) && (t >= __ldg(a.lens + b));
+    const bool masked = (a.lens != nullptr) && (b < a.B) && (t < a.To) && (t >= __ldg(a.lens + b));
     const int ncols = min(BN, a.Cout - n0);
     const int ngroups = (ncols + (int)EPC - 1) / (int)EPC;
     const float scale = a.out_scale, aslope = a.act_slope_eff;
@@ -381,7 +392,10 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * wg) : "memory");
+    if (lane == 0) {
+      if (remote_tempty) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty0 + 8u * wg) : "memory");
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * wg) : "memory");
+    }
   }
   if (lane == 0) bulk_wait_all0();   // all stores complete before the CTA exits
 }
@@ -512,6 +526,182 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2) for 256-wide tiles.  ncu on the 1-CTA kernel: the stage-0 vocoder convs and
+// every mid-size acoustic GEMM are L2->SM-bandwidth-bound with 128 x 256 tiles (each CTA pulls 16 KB of
+// activations + 32 KB of weights per K step, ~57 B/clk/SM).  Here a cluster of two CTAs (a TPC pair)
+// computes a 256 x 256 tile: each CTA loads ITS 128 rows of activations and HALF of the weight tile
+// (128 of the 256 output channels); the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads
+// both halves from the two CTAs' shared memory and writes each CTA's 128 rows into that CTA's TMEM.
+// 32 KB per CTA per K step instead of 48 KB.  Barriers: TMA loads of both CTAs complete on the LEADER's
+// full barrier; the leader's commits multicast to both CTAs' empty / tfull barriers; both CTAs'
+// epilogue warps arrive on the leader's tempty barrier.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BK, bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CV_THREADS, 1)
+conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+                       const __grid_constant__ EpiMaps emaps, const __grid_constant__ ConvArgs a) {
+  constexpr int BN = 256;
+  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int WH_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the weight tile
+  constexpr int STAGE_BYTES = A_BYTES + WH_BYTES;
+  constexpr int TMEM_COLS = 512;
+
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int S = a.stages;
+  const uint32_t bar_base = smem_base + S * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bar_base + 8u * (2 * S + 6) - smem_u32(smem_dyn)));
+  for (int i = threadIdx.x; i < a.CoutP; i += blockDim.x) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? a.bias[i] : 0.f;
+  const uint32_t epi_base = (bar_base + 8u * (2 * S + 6) + (uint32_t)a.CoutP * 4u + 1023u) & ~1023u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = a.B * a.n_ttiles * a.n_ftiles;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_super = m_pairs * (a.CoutP / BN);
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int k_iters = a.ntaps * a.kchunks;
+
+  if (threadIdx.x == 0) {
+    // full: one arrive (the leader's expect_tx) + the bytes of both CTAs; empty / tfull: the leader's commits;
+    // tempty (used in the leader only): 4 epilogue warps of each CTA
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+    if (a.epi_tma) for (int i = 0; i < 8; ++i) mbar_init(epi_base + 8u * epi_warp_bytes(BN) + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWh) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();            // both CTAs' barriers are initialised and their TMEM is allocated (also a CTA barrier)
+  tc_fence_after();
+  pdl_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own activation rows + own half of the weight tile =====
+      int it = 0;
+      for (int st = cid; st < total_super; st += n_clusters) {
+        int mt = (st % m_pairs) * 2 + (int)rank;
+        const int n0 = (st / m_pairs) * BN;
+        const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
+        const int tt = mt % a.n_ttiles; mt /= a.n_ttiles;
+        const int b = mt, t0 = tt * a.tT, f0 = ft * a.tF;          // b == B for the padding tile: zero-filled by TMA
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (leader) mbar_expect_tx(full_bar(s), 2u * STAGE_BYTES);
+          const uint32_t fb = mapa_u32(full_bar(s), 0);            // the leader's full barrier
+          const int tap = kit / a.kchunks, kc = kit - tap * a.kchunks;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          tma2_load_4d(sa, &tmA, fb, kc * BK, f0 + a.tap_df[tap], t0 + a.tap_dt[tap], b);
+          tma2_load_2d(sa + A_BYTES, &tmWh, fb, kc * BK, tap * a.CoutP + n0 + (int)rank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      // ===== MMA issuer (leader CTA only) =====
+      int it = 0, lt = 0;
+      for (int st = cid; st < total_super; st += n_clusters, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint64_t da = make_smem_desc<BK>(sa);
+          const uint64_t db = make_smem_desc<BK>(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc2_mma_f16(tacc, da + uint64_t(2 * k), db + uint64_t(2 * k), a.idesc, (kit | k) != 0 ? 1u : 0u);
+          tc2_commit(empty_bar(s));
+        }
+        tc2_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (both CTAs, each on its own 128 rows): arrives on the leader's tempty barriers =====
+    const uint32_t tempty_leader = mapa_u32(tempty_bar(0), 0);
+    if (a.epi_tma)
+      run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_leader, warp, lane, m_pairs, total_super, bias_s, epi_base,
+                                 cid, n_clusters, 2, (int)rank, true);
+    else
+      run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_leader, warp, lane, m_pairs, total_super, bias_s,
+                             cid, n_clusters, 2, (int)rank, true);
+  }
+
+  tc_fence_before();
+  cluster_sync();            // the peer may still multicast commits into this CTA / read its operands
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Narrow-channel 1-D variant (Cin, Cout <= 64: vocoder stages with 64 / 32 channels, 37 % of its
@@ -824,6 +1014,31 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const EpiMaps& e
   if (grid > total_tiles) grid = total_tiles;
   ASB_CUDA(launch_k(conv_igemm_kernel<BN, BK, BF16>, grid, CV_THREADS, smem, st, tmA, tmW, em, a));
   ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
+template <int BK, bool BF16>
+int launch_conv_2cta(const CUtensorMap& tmA, const CUtensorMap& tmWh, const EpiMaps& em, ConvArgs& a, cudaStream_t st) {
+  constexpr int BN = 256;
+  constexpr int STAGE_BYTES = 128 * BK * 2 + (BN / 2) * BK * 2;
+  const int budget = a.epi_tma ? (222 * 1024 - (int)epi_bytes(BN) - 2048 - a.CoutP * 4) : (208 * 1024 - a.CoutP * 4);
+  int stages = budget / STAGE_BYTES;
+  if (stages > 12) stages = 12;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  a.idesc = (a.idesc & ~(0x1Fu << 24)) | (uint32_t(256 >> 4) << 24);      // UMMA M = 256 across the CTA pair
+  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
+                      (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_2cta_kernel<BK, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int m_tiles = a.B * a.n_ttiles * a.n_ftiles;
+  const int total_super = ((m_tiles + 1) / 2) * (a.CoutP / BN);
+  int clusters = num_sms() / 2;
+  if (clusters > total_super) clusters = total_super;
+  ASB_CUDA(launch_k(conv_igemm_2cta_kernel<BK, BF16>, 2 * clusters, CV_THREADS, smem, st, tmA, tmWh, em, a));
   return AS_OK;
 }
 

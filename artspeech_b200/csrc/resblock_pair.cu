@@ -464,6 +464,8 @@ static int launch_pair(const PairMaps& maps, const PairArgs& a, size_t smem, cud
     attr_set = true;
   }
   int grid = num_sms();
+  static const int grid_cap = getenv("ASB_PAIR_GRID") ? atoi(getenv("ASB_PAIR_GRID")) : 0;   // experiments: leave SMs to concurrent streams
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   if (grid > a.total_tiles) grid = a.total_tiles;
   ASB_CUDA(launch_k(resblock_pair_kernel<C, BF16>, grid, RP_THREADS, smem, st, maps, a));
   ASB_CUDA(cudaGetLastError());

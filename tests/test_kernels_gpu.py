@@ -103,6 +103,32 @@ def test_resblock_pair(shape, variant, dt):
     assert torch.count_nonzero(out.cpu()[0, lens[0]:]) == 0 and torch.count_nonzero(out.cpu()[-1, lens[-1]:]) == 0
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 2500, 256, 512, 3, 1), (3, 1700, 512, 256, 5, 2), (1, 9000, 128, 1024, 1, 1),
+                                   (5, 1153, 320, 768, 3, 1)])
+def test_conv_igemm_2cta_pairs(shape, dt):
+    """Shapes large enough for 256-wide tiles: the cta_group::2 kernel (CTA pairs sharing the weight tile),
+    including odd numbers of M-tiles (padding tile), ragged lengths, residuals and both output kinds."""
+    B, T, Cin, Cout, k, dil = shape
+    torch.manual_seed(5)
+    x = (torch.randn(B, T, Cin) * 0.5).to(dt)
+    w = torch.randn(k, Cout, Cin) / (Cin * k) ** 0.5
+    bias = torch.randn(Cout)
+    r1 = torch.randn(B, T, Cout)
+    lens = _lens(B, T)
+    pw_c = ops.pack_conv(w, bias, ops.taps_1d(k, dil), dt, "cpu")
+    pw_g = ops.pack_conv(w, bias, ops.taps_1d(k, dil), dt, DEV)
+    ref_raw, ref_act = sim.conv(x, pw_c, res1=r1, scale=0.7, raw=torch.float32, act_out=dt, act=ops.ACT_LRELU, slope=0.2, lens=lens)
+    raw, act = ops.conv(x.to(DEV), pw_g, res1=r1.to(DEV), scale=0.7, raw=torch.float32, act_out=dt, act=ops.ACT_LRELU,
+                        slope=0.2, lens=lens.to(DEV))
+    _close(raw, ref_raw, 2e-4, "raw")
+    _close(act, ref_act, 1e-2 if dt == torch.bfloat16 else 2e-3, "act")
+    # all-16-bit outputs take the TMA epilogue
+    ref16, _ = sim.conv(x, pw_c, res1=r1.to(dt), raw=dt, lens=lens)
+    out16, _ = ops.conv(x.to(DEV), pw_g, res1=r1.to(dt).to(DEV), raw=dt, lens=lens.to(DEV))
+    _close(out16, ref16, 1e-2 if dt == torch.bfloat16 else 2e-3, "raw16")
+
+
 @pytest.mark.parametrize("shape", [(2, 70, 80, 64, 64, 3, 3), (1, 33, 40, 128, 128, 3, 3), (2, 50, 10, 64, 128, 3, 3),
                                    (1, 15, 5, 512, 512, 5, 5)])
 def test_conv_igemm_2d(shape):

@@ -10,11 +10,12 @@
 namespace asb {
 
 // ---------------------------------------------------------------------------------------------
-// relpos attention.  CTA = 8 warps, each warp owns QW = 2 consecutive queries of one (b, h);
-// K / V tiles of 32 keys are staged in shared memory and shared by the CTA's 16 queries.
+// relpos attention.  CTA = 8 warps, each warp owns QW = 4 consecutive queries of one (b, h);
+// K / V tiles of 32 keys are staged in shared memory and shared by the CTA's 32 queries (float4 inner loops:
+// one 16-byte key load + QW broadcast query loads per 4 x QW FMAs).
 // ---------------------------------------------------------------------------------------------
 constexpr int RA_WARPS = 8;
-constexpr int RA_QW = 2;
+constexpr int RA_QW = 4;
 constexpr int RA_QT = RA_WARPS * RA_QW;  // queries per CTA
 constexpr int RA_KT = 32;                // keys per tile
 constexpr int RA_MAXW = 9;               // 2*window+1 <= 9
@@ -26,7 +27,7 @@ relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float
                         const int* __restrict__ lens, void* out, int odt, long long out_ld) {
   pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   extern __shared__ float sm[];
-  constexpr int KP = D + 1;                 // padded pitch: conflict-free row reads
+  constexpr int KP = D + 4;                 // padded pitch: 16-byte aligned, conflict-free float4 row reads
   float* kv = sm;                           // [RA_KT][KP]
   float* qs = kv + RA_KT * KP;              // [RA_QT][D]
   float* qe = qs + RA_QT * D;               // [RA_QT][RA_MAXW] q . E_k[r]
@@ -80,10 +81,14 @@ relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float
 #pragma unroll
     for (int u = 0; u < RA_QW; ++u) s[u] = 0.f;
     const float* kr = kv + lane * KP;
-    for (int d = 0; d < D; ++d) {
-      const float kd = kr[d];
+#pragma unroll 4
+    for (int d = 0; d < D; d += 4) {
+      const float4 kd = *reinterpret_cast<const float4*>(kr + d);
 #pragma unroll
-      for (int u = 0; u < RA_QW; ++u) s[u] += qs[(warp * RA_QW + u) * D + d] * kd;
+      for (int u = 0; u < RA_QW; ++u) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + (warp * RA_QW + u) * D + d);
+        s[u] += q4.x * kd.x + q4.y * kd.y + q4.z * kd.z + q4.w * kd.w;
+      }
     }
 #pragma unroll
     for (int u = 0; u < RA_QW; ++u) {
@@ -407,7 +412,7 @@ extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float
   ASB_REQUIRE(D == 128, AS_ERR_SHAPE, "as_relpos_attention: head dim %d unsupported (128 only)", D);
   ASB_REQUIRE(window >= 0 && 2 * window + 1 <= RA_MAXW, AS_ERR_SHAPE, "as_relpos_attention: window");
   const int Tpad = (T + 31) & ~31;
-  const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 1) + RA_QT * D + RA_QT * RA_MAXW + (size_t)RA_QT * Tpad);
+  const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 4) + RA_QT * D + RA_QT * RA_MAXW + (size_t)RA_QT * Tpad);
   ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_relpos_attention: T=%d too long for the score buffer", T);
   static bool attr = false;
   if (!attr) {

@@ -10,7 +10,7 @@ import os
 
 from . import build as _build
 
-AS_F16, AS_BF16, AS_F32 = 0, 1, 2
+AS_F16, AS_BF16, AS_F32, AS_PCM16 = 0, 1, 2, 3
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SWISH, ACT_ABS = 0, 1, 2, 3, 4, 5
 
 c_i32_p = C.POINTER(C.c_int32)
@@ -125,4 +125,6 @@ SIGNATURES.update({
     "as_log_norm": (C.c_int, [_V, _I, _I, _I, _V, _V]),
     "as_log_mel": (C.c_int, [_V, _L, _V, _I, _I, _V, _V, _V, _V, _I, _I, _I, _F, _F, _F, _V, _I, _V]),
     "as_transpose_cast": (C.c_int, [_V, _I, _V, _I, _I, _I, _I, _L, _I, _V, _V, _V, _V]),
+    "as_mas_align": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _V, C.c_size_t, _V]),
+    "as_expand_tokens": (C.c_int, [_V, _V, _V, _I, _I, _I, _I, _V]),
 })

@@ -74,13 +74,20 @@ conv_cout1_kernel(const uint16_t* __restrict__ x, long long x_ld, int T, int Cin
     if (lens != nullptr && t >= lens[b]) v = 0.f;
     const long long row = (long long)b * T + t;
     if (y_raw) stany(y_raw, row * y_raw_ld, v, y_raw_dtype);
-    if (y_act) stany(y_act, row * y_act_ld, apply_act(v, act, slope), y_act_dtype);
+    if (y_act) {
+      const float a = apply_act(v, act, slope);
+      if (y_act_dtype == AS_PCM16)   // libsndfile's float -> PCM_16: lrint(32767 * x) (test.py:119), saturated
+        reinterpret_cast<int16_t*>(y_act)[row * y_act_ld] = (int16_t)max(-32768, min(32767, __float2int_rn(a * 32767.f)));
+      else
+        stany(y_act, row * y_act_ld, a, y_act_dtype);
+    }
   }
 }
 
 // eligible: 1-D, one output channel, 16-bit input with Cin % 8 == 0 and Cin <= 64, equally spaced taps, no residuals
 bool conv_cout1_eligible(const as_conv_params* p) {
   if (p->Cout != 1 || p->F != 1 || p->Fo != 1 || p->To != p->T || p->res1 || p->res2 || p->stats) return false;
+  if (p->y_raw && p->y_raw_dtype == AS_PCM16) return false;    // PCM is an activated-output format only
   if (p->Cin % 8 != 0 || p->Cin > 64 || p->ntaps > 16 || (p->x_ld % 8) != 0) return false;
   const int dil = p->ntaps > 1 ? p->tap_dt[1] - p->tap_dt[0] : 1;
   if (dil < 1) return false;

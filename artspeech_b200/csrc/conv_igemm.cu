@@ -149,6 +149,8 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
   if (rc != AS_OK) return rc;
   static const bool no_cout1 = getenv("ASB_NO_COUT1") != nullptr;
   if (!no_cout1 && conv_cout1_eligible(p)) return conv_cout1_launch(p, reinterpret_cast<cudaStream_t>(stream));
+  ASB_REQUIRE(!(p->y_act && p->y_act_dtype == AS_PCM16) && !(p->y_raw && p->y_raw_dtype == AS_PCM16), AS_ERR_DTYPE,
+              "as_conv_igemm: AS_PCM16 output is only available for single-output-channel 1-D convolutions");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return AS_ERR_CUDA;
 

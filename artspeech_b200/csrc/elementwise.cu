@@ -502,6 +502,154 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
   }
 }
 
+// Wide-row cluster variant (the one the decoder's shapes take).  The 32-channel slabs above make every CTA read
+// 128-byte pieces 4 KB apart: DRAM pages are opened for 128 bytes at a time and the pass saturates near 2.9 TB/s
+// whatever the CTA-level overlap is (a persistent multi-stage ring of the same slabs measured no faster).  Here a
+// thread-block CLUSTER of CS CTAs owns 128 channels of one item -- 512 contiguous bytes per row -- and splits the
+// frames: CTA r keeps rows [r*TR, (r+1)*TR) in shared memory (one or two TMA boxes), partial sums / squared
+// deviations are exchanged through distributed shared memory around two cluster barriers (exact two-pass
+// statistics), and every warp instruction then writes one 256-byte row segment of the 16-bit output.
+constexpr int ADW_CW = 128;               // channels per cluster
+constexpr int ADW_SLAB_BYTES = 110 * 1024;
+
+__device__ __forceinline__ float4 adw_ld_peer4(const float* p, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
+template <bool UP, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(256)
+adain_wide_kernel(const __grid_constant__ CUtensorMap tmx, int T, int TR, int BR, int nbox, int C,
+                  const float* __restrict__ gb, long long gb_ld, float eps, float slope,
+                  const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
+                  void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
+  extern __shared__ __align__(128) float slab_raw[];
+  __shared__ __align__(16) float red[8][ADW_CW];
+  __shared__ __align__(16) float part[2][ADW_CW];          // this CTA's partial sum / partial squared deviation
+  __shared__ __align__(8) unsigned long long bar_storage;
+  float* slab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(slab_raw) + 127) & ~uintptr_t(127));   // [nbox*BR][128]
+  const uint32_t bar = smem_u32(&bar_storage);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t rank = CS == 1 ? 0u : adf_cluster_rank();
+  const int b = blockIdx.y, cb = (blockIdx.x / CS) * ADW_CW, c = cb + 4 * lane;
+  const bool cok = c < C;                                   // C % 4 == 0: a quad is all-in or all-out
+  const int len = lens ? min(lens[b], T) : T;
+  const int t_lo = (int)rank * TR;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)nbox * BR * (ADW_CW * 4u));
+    for (int k = 0; k < nbox; ++k) tma_load_3d(smem_u32(slab) + (uint32_t)k * BR * (ADW_CW * 4u), &tmx, bar, cb, t_lo + k * BR, b);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const int nv = max(0, min(len - t_lo, TR));               // rows of this CTA that enter the statistics
+  auto cluster_total = [&](float4 p, int which) -> float4 {
+    *reinterpret_cast<float4*>(&red[w][4 * lane]) = p;
+    __syncthreads();
+    if (w == 0) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(&red[i][4 * lane]);
+        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+      }
+      *reinterpret_cast<float4*>(&part[which][4 * lane]) = t;
+    }
+    if (CS == 1) __syncthreads(); else adf_cluster_sync();   // partials of every CTA of the cluster are published
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {
+      const float4 q = CS == 1 ? *reinterpret_cast<const float4*>(&part[which][4 * lane]) : adw_ld_peer4(&part[which][4 * lane], (uint32_t)r);
+      t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+    }
+    return t;
+  };
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = w; t < nv; t += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(slab + t * ADW_CW + 4 * lane);
+    s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+  }
+  const float inv_len = len > 0 ? 1.f / len : 0.f;
+  float4 mean = cluster_total(s4, 0);
+  mean.x *= inv_len; mean.y *= inv_len; mean.z *= inv_len; mean.w *= inv_len;
+  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = w; t < nv; t += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(slab + t * ADW_CW + 4 * lane);
+    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+    q4.x += dx * dx; q4.y += dy * dy; q4.z += dz * dz; q4.w += dw * dw;
+  }
+  const float4 var = cluster_total(q4, 1);
+  // peers may still be reading this CTA's partials: arrive now, wait right before exit
+  if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  if (cok) {
+    const float4 rstd = make_float4(rsqrtf(var.x * inv_len + eps), rsqrtf(var.y * inv_len + eps),
+                                    rsqrtf(var.z * inv_len + eps), rsqrtf(var.w * inv_len + eps));
+    if (stats_out != nullptr && rank == 0 && w == 0) {
+      float* so = stats_out + ((long long)b * C + c) * 2;
+      so[0] = mean.x; so[1] = rstd.x; so[2] = mean.y; so[3] = rstd.y; so[4] = mean.z; so[5] = rstd.z; so[6] = mean.w; so[7] = rstd.w;
+    }
+    const float4 g = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + c);
+    const float4 be = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + C + c);
+    const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
+    auto act_at = [&](int t) -> float4 {     // t: absolute frame; rows t_lo .. t_lo + TR (+1 halo row when UP) are resident
+      if (t >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v = *reinterpret_cast<const float4*>(slab + (t - t_lo) * ADW_CW + 4 * lane);
+      v.x = (v.x - mean.x) * sc.x + be.x; v.y = (v.y - mean.y) * sc.y + be.y;
+      v.z = (v.z - mean.z) * sc.z + be.z; v.w = (v.w - mean.w) * sc.w + be.w;
+      v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+      v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      return v;
+    };
+    const int t_end = min(T, t_lo + TR);
+    if (!UP) {
+#pragma unroll 4
+      for (int t = t_lo + w; t < t_end; t += 8) st4any(out, ((long long)b * T + t) * out_ld + c, act_at(t), odt);
+    } else {
+      float w0[4], w1[4], w2[4], ub[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
+      for (int t = t_lo + w; t < t_end; t += 8) {
+        float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
+        if (t < len) {
+          const float4 a0 = act_at(t), a1 = act_at(t + 1);
+          ev = make_float4(a0.x * w1[0] + ub[0], a0.y * w1[1] + ub[1], a0.z * w1[2] + ub[2], a0.w * w1[3] + ub[3]);
+          od = make_float4(a0.x * w2[0] + a1.x * w0[0] + ub[0], a0.y * w2[1] + a1.y * w0[1] + ub[1],
+                           a0.z * w2[2] + a1.z * w0[2] + ub[2], a0.w * w2[3] + a1.w * w0[3] + ub[3]);
+        }
+        st4any(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
+        st4any(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+      }
+    }
+  }
+  if (CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// expansion of token columns along a monotonic alignment: out[b, c, y] = x[b, c, tok[b, y]]
+// (= x @ path for a 0/1 path with one 1 per column).  One warp-row per (b, c): writes coalesced along y,
+// reads walk the row of x monotonically (every 128-byte line is fetched once and re-served by L1).
+// ---------------------------------------------------------------------------------------------
+__global__ void expand_tokens_kernel(const float* __restrict__ x, const int* __restrict__ tok, float* __restrict__ out,
+                                     long long rows, int C, int Tx, int Ty) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
+  const long long total = rows * Ty;
+  ASB_GRID_STRIDE(i, total, {
+    const int y = i % Ty;
+    const long long bc = i / Ty;
+    const int t = tok[(bc / C) * Ty + y];
+    out[i] = (t >= 0 && t < Tx) ? x[bc * Tx + t] : 0.f;
+  })
+}
+
 // ---------------------------------------------------------------------------------------------
 // nearest upsample along T
 // ---------------------------------------------------------------------------------------------
@@ -625,6 +773,9 @@ __global__ void conv_small_kernel(const void* __restrict__ x, int xdt, long long
 // 8 output channels per thread, weights transposed to [tap][ci][co] in shared memory, 32-bit index
 // arithmetic (the scalar kernel above spends its time in 64-bit div/mod: 530 us for the 1 -> 64
 // channel 3x3 stems of JDCNet / Mel_block on a 16 x 240 x 80 image).
+// P consecutive F positions per thread (P = 4 when F % 4 == 0): a weight octet read from shared memory and the
+// row / bounds arithmetic of a tap are shared by the P positions.
+template <int P>
 __global__ void __launch_bounds__(256)
 conv_small_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T, int F, int Cin,
                       const float* __restrict__ w, const float* __restrict__ bias, int ntaps, SmallTaps taps,
@@ -641,34 +792,37 @@ conv_small_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B
   __syncthreads();
   const int groups = Cout >> 3;
   const unsigned rows = (unsigned)B * T * F;            // host guarantees rows * groups < 2^31
-  const unsigned total = rows * groups;
+  const unsigned total = rows / P * groups;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned g = i % groups, row = i / groups;
+    const unsigned g = i % groups, row = i / groups * P;
     const int f = row % F;
     const unsigned bt = row / F;
     const int t = bt % T, b = bt / T;
     const int co = g * 8;
-    float acc[8];
+    float acc[P][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = ws[nw + co + e];
+    for (int q = 0; q < P; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[q][e] = ws[nw + co + e];
     for (int j = 0; j < ntaps; ++j) {
-      const int ti = t + taps.dt[j], fi = f + taps.df[j];
-      if (ti < 0 || ti >= T || fi < 0 || fi >= F) continue;
-      const long long xr = (((long long)b * T + ti) * F + fi) * x_ld;
+      const int ti = t + taps.dt[j], f0 = f + taps.df[j];
+      if (ti < 0 || ti >= T) continue;
+      const long long xr = (((long long)b * T + ti) * F + f0) * x_ld;
       for (int ci = 0; ci < Cin; ++ci) {
-        const float xv = ldany(x, xr + ci, xdt);
         const float4 w0 = *reinterpret_cast<const float4*>(ws + (j * Cin + ci) * Cout + co);
         const float4 w1 = *reinterpret_cast<const float4*>(ws + (j * Cin + ci) * Cout + co + 4);
-        acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
-        acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          const int fi = f0 + q;
+          const float xv = (fi >= 0 && fi < F) ? ldany(x, xr + q * x_ld + ci, xdt) : 0.f;
+          acc[q][0] += xv * w0.x; acc[q][1] += xv * w0.y; acc[q][2] += xv * w0.z; acc[q][3] += xv * w0.w;
+          acc[q][4] += xv * w1.x; acc[q][5] += xv * w1.y; acc[q][6] += xv * w1.z; acc[q][7] += xv * w1.w;
+        }
       }
     }
-    if (lens && t >= lens[b]) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    }
-    auto put = [&](void* y, int dt, long long ld, int vec, const float (&v)[8]) {
-      const long long o = (long long)row * ld + co;
+    const bool dead = lens && t >= lens[b];
+    auto put = [&](void* y, int dt, long long ld, int vec, unsigned r, const float (&v)[8]) {
+      const long long o = (long long)r * ld + co;
       if (vec && dt != AS_F32) {
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + o) =
             make_uint4(pack16(v[0], v[1], dt), pack16(v[2], v[3], dt), pack16(v[4], v[5], dt), pack16(v[6], v[7], dt));
@@ -680,12 +834,19 @@ conv_small_vec_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B
         for (int e = 0; e < 8; ++e) stany(y, o + e, v[e], dt);
       }
     };
-    if (yr) put(yr, yrdt, yr_ld, vec_raw, acc);
-    if (ya) {
-      float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = apply_act(acc[e], act, slope);
-      put(ya, yadt, ya_ld, vec_act, v);
+    for (int q = 0; q < P; ++q) {
+      if (dead) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
+      }
+      if (yr) put(yr, yrdt, yr_ld, vec_raw, row + q, acc[q]);
+      if (ya) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = apply_act(acc[q][e], act, slope);
+        put(ya, yadt, ya_ld, vec_act, row + q, v);
+      }
     }
   }
 }
@@ -828,6 +989,126 @@ __global__ void affine_act_maxpool_kernel(const void* __restrict__ x, int xdt, l
 }
 
 // ---------------------------------------------------------------------------------------------
+// 8-channel (16-byte) variants of the strided depthwise conv / average pool / affine+LeakyReLU+max pool for 16-bit
+// channels-last tensors: the scalar kernels above issue one 2-byte load and a chain of 64-bit div/mods per
+// element (dwconv 120 us, pools 47 us on the 16 x 240 x 80 x 64 style-encoder images -- 10x off the HBM time).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8h(const void* p, long long off, int dt, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + off));
+  const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (dt == AS_BF16) {
+      v[2 * e] = __uint_as_float(q[e] << 16); v[2 * e + 1] = __uint_as_float(q[e] & 0xFFFF0000u);
+    } else {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q[e]));
+      v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void st8h(void* p, long long off, const float (&v)[8], int dt) {
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p) + off) =
+      make_uint4(pack16(v[0], v[1], dt), pack16(v[2], v[3], dt), pack16(v[4], v[5], dt), pack16(v[6], v[7], dt));
+}
+
+__global__ void __launch_bounds__(256)
+dwconv_vec8_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T, int F, int C,
+                   const float* __restrict__ w, const float* __restrict__ bias, int kt, int kf, int st, int sf, int pt,
+                   int pf, int To, int Fo, const int* __restrict__ lens_in, const int* __restrict__ lens_out, int act,
+                   float slope, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
+  const unsigned groups = (unsigned)C >> 3;
+  const unsigned total = (unsigned)B * To * Fo * groups;     // host guarantees < 2^31
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned g = i % groups, row = i / groups;
+    const int fo = row % Fo;
+    const unsigned bto = row / Fo;
+    const int to = bto % To, b = bto / To;
+    const int c = g * 8;
+    const int len_in = lens_in ? min(lens_in[b], T) : T;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[c + e] : 0.f;
+    for (int jt = 0; jt < kt; ++jt) {
+      const int ti = to * st + jt - pt;
+      if (ti < 0 || ti >= len_in) continue;
+      for (int jf = 0; jf < kf; ++jf) {
+        const int fi = fo * sf + jf - pf;
+        if (fi < 0 || fi >= F) continue;
+        float v[8];
+        ld8h(x, (((long long)b * T + ti) * F + fi) * x_ld + c, xdt, v);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (jt * kf + jf) * C + c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (jt * kf + jf) * C + c + 4));
+        acc[0] += v[0] * w0.x; acc[1] += v[1] * w0.y; acc[2] += v[2] * w0.z; acc[3] += v[3] * w0.w;
+        acc[4] += v[4] * w1.x; acc[5] += v[5] * w1.y; acc[6] += v[6] * w1.z; acc[7] += v[7] * w1.w;
+      }
+    }
+    const bool dead = lens_out && to >= lens_out[b];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = dead ? 0.f : apply_act(acc[e], act, slope);
+    st8h(out, (long long)row * out_ld + c, acc, odt);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+avgpool_vec8_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T, int F, int C, int pt, int pf,
+                    int To, int Fo, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
+  const unsigned groups = (unsigned)C >> 3;
+  const unsigned total = (unsigned)B * To * Fo * groups;
+  const float inv = 1.f / (pt * pf);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned g = i % groups, row = i / groups;
+    const int fo = row % Fo;
+    const unsigned bto = row / Fo;
+    const int to = bto % To, b = bto / To;
+    const int c = g * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int jt = 0; jt < pt; ++jt) {
+      const int ti = min(to * pt + jt, T - 1);  // replicate the last column when T is odd
+      for (int jf = 0; jf < pf; ++jf) {
+        float v[8];
+        ld8h(x, (((long long)b * T + ti) * F + fo * pf + jf) * x_ld + c, xdt, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    st8h(out, (long long)row * out_ld + c, acc, odt);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+affine_act_maxpool_vec8_kernel(const void* __restrict__ x, int xdt, long long x_ld, int B, int T, int F, int C,
+                               const float* __restrict__ scale, const float* __restrict__ shift, float slope, int pf,
+                               int Fo, void* out, int odt, long long out_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
+  const unsigned groups = (unsigned)C >> 3;
+  const unsigned total = (unsigned)B * T * Fo * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned g = i % groups, row = i / groups;
+    const int fo = row % Fo;
+    const unsigned bt = row / Fo;
+    const int c = g * 8;
+    float sc[8], sh[8], m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = scale[c + e]; sh[e] = shift[c + e]; m[e] = -INFINITY; }
+    for (int j = 0; j < pf; ++j) {
+      float v[8];
+      ld8h(x, ((long long)bt * F + fo * pf + j) * x_ld + c, xdt, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float y = v[e] * sc[e] + sh[e];
+        y = y > 0.f ? y : y * slope;
+        m[e] = fmaxf(m[e], y);
+      }
+    }
+    st8h(out, (long long)row * out_ld + c, m, odt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LeakyReLU + global average pool over (T with stride, F)
 // ---------------------------------------------------------------------------------------------
 __global__ void global_avgpool_kernel(const void* __restrict__ x, int xdt, long long x_ld, int T, int F,
@@ -931,6 +1212,12 @@ __global__ void transpose_cast_kernel(const void* __restrict__ src, int sdt, voi
   }
 }
 
+// 16-bit in / out, 8-channel groups on 16-byte boundaries, 32-bit element counts
+static inline bool vec8_ok(const void* x, int xdt, long long x_ld, const void* out, int odt, long long out_ld, int C, long long total) {
+  return xdt != AS_F32 && odt != AS_F32 && (C % 8) == 0 && (x_ld % 8) == 0 && (out_ld % 8) == 0 &&
+         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && total < (1ll << 31);
+}
+
 static inline unsigned ew_grid(long long total, int threads = 256) {
   long long g = (total + threads - 1) / threads;
   const long long cap = 148LL * 16;  // a few waves of the 148 SMs, grid-stride beyond that
@@ -1032,6 +1319,45 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
                               return (reinterpret_cast<uintptr_t>(out) % (4 * es)) == 0 && ((out_ld * es) % (4 * es)) == 0; }() &&
       (reinterpret_cast<uintptr_t>(gb) & 15) == 0 && (gb_ld % 4) == 0 && check_arch() == AS_OK) {
     EncodeTiledFn enc = get_encode_fn();
+    static const bool no_wide = getenv("ASB_ADAIN_NO_WIDE") != nullptr;
+    if (enc && !no_wide && C >= ADW_CW) {
+      // smallest cluster whose per-CTA row range (+1 halo row for the transposed depthwise "pool") fits two CTAs per SM
+      int CS = 1;
+      auto rows_need = [&](int cs) { return (T + cs - 1) / cs + (up_w ? 1 : 0); };
+      while (CS < 8 && (size_t)rows_need(CS) * ADW_CW * 4 > (size_t)ADW_SLAB_BYTES) CS <<= 1;
+      if ((size_t)rows_need(CS) * ADW_CW * 4 <= (size_t)ADW_SLAB_BYTES) {
+        const int TR = (T + CS - 1) / CS, need = rows_need(CS);
+        const int nbox = (need + 255) / 256, BR = (need + nbox - 1) / nbox;
+        CUtensorMap tmx;
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)x_ld * 4, (cuuint64_t)x_ld * 4 * T};
+        cuuint32_t box[3] = {(cuuint32_t)ADW_CW, (cuuint32_t)BR, 1};
+        cuuint32_t es3[3] = {1, 1, 1};
+        if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+          const size_t smem = (size_t)nbox * BR * ADW_CW * 4 + 128;
+          dim3 grid(cdiv(C, ADW_CW) * CS, (unsigned)B);
+#define ADW_LAUNCH(UP_, CS_)                                                                                                   \
+  do {                                                                                                                         \
+    static bool attr = false;                                                                                                  \
+    if (!attr) {                                                                                                               \
+      ASB_CUDA(cudaFuncSetAttribute(adain_wide_kernel<UP_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADW_SLAB_BYTES + 1024)); \
+      attr = true;                                                                                                             \
+    }                                                                                                                          \
+    ASB_CUDA(launch_k(adain_wide_kernel<UP_, CS_>, grid, 256, smem, ST(stream), tmx, T, TR, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, \
+                      up_b, out, out_dtype, out_ld, stats));                                                                   \
+  } while (0)
+          if (up_w) {
+            if (CS == 1) ADW_LAUNCH(true, 1); else if (CS == 2) ADW_LAUNCH(true, 2); else if (CS == 4) ADW_LAUNCH(true, 4); else ADW_LAUNCH(true, 8);
+          } else {
+            if (CS == 1) ADW_LAUNCH(false, 1); else if (CS == 2) ADW_LAUNCH(false, 2); else if (CS == 4) ADW_LAUNCH(false, 4); else ADW_LAUNCH(false, 8);
+          }
+#undef ADW_LAUNCH
+          ASB_CUDA(cudaGetLastError());
+          return AS_OK;
+        }
+      }
+    }
     if (enc) {
       const int nbox = (T + 255) / 256;
       const int BR = ((T + nbox - 1) / nbox + 7) / 8 * 8;
@@ -1042,7 +1368,8 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
       cuuint32_t es3[3] = {1, 1, 1};
       if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-        const size_t smem = (size_t)nbox * BR * 128 + 128;
+        const size_t slab_bytes = (size_t)nbox * BR * 128;
+        const size_t smem = slab_bytes + 128;
         static bool attr = false;
         if (!attr) {
           ASB_CUDA(cudaFuncSetAttribute(adain_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
@@ -1101,6 +1428,18 @@ extern "C" int as_repeat_rows(const void* x, int32_t x_dtype, int64_t x_ld, int3
   return AS_OK;
 }
 
+extern "C" int as_expand_tokens(const float* x, const int32_t* token_of_frame, float* out, int32_t B, int32_t C,
+                                int32_t Tx, int32_t Ty, void* stream) {
+  const long long total = (long long)B * C * Ty;
+  if (total == 0) return AS_OK;
+  ASB_REQUIRE(x && token_of_frame && out && Tx > 0, AS_ERR_SHAPE, "as_expand_tokens: bad argument");
+  int rc = check_arch();
+  if (rc != AS_OK) return rc;
+  ASB_CUDA(launch_k(expand_tokens_kernel, ew_grid(total), 256, 0, ST(stream), x, token_of_frame, out, (long long)B * C, C, Tx, Ty));
+  ASB_CUDA(cudaGetLastError());
+  return AS_OK;
+}
+
 extern "C" int as_length_regulate(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, int32_t Tt,
                                   int32_t C, const int32_t* dur, const int32_t* lens_t, int32_t rep,
                                   int32_t To, void* out, int32_t out_dtype, int64_t out_ld,
@@ -1142,9 +1481,14 @@ extern "C" int as_conv_small(const void* x, int32_t x_dtype, int64_t x_ld, int32
     auto al16 = [](const void* ptr, long long ld, int dt) {
       return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld * (dt == AS_F32 ? 4 : 2)) & 15) == 0;
     };
-    ASB_CUDA(launch_k(conv_small_vec_kernel, ew_grid(total / 8), 256, wsmem, ST(stream), 
-        x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps, Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
-        y_act_dtype, y_act_ld, act, slope, al16(y_raw, y_raw_ld, y_raw_dtype) ? 1 : 0, al16(y_act, y_act_ld, y_act_dtype) ? 1 : 0));
+    if ((F % 4) == 0)
+      ASB_CUDA(launch_k(conv_small_vec_kernel<4>, ew_grid(total / 32), 256, wsmem, ST(stream),
+          x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps, Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
+          y_act_dtype, y_act_ld, act, slope, al16(y_raw, y_raw_ld, y_raw_dtype) ? 1 : 0, al16(y_act, y_act_ld, y_act_dtype) ? 1 : 0));
+    else
+      ASB_CUDA(launch_k(conv_small_vec_kernel<1>, ew_grid(total / 8), 256, wsmem, ST(stream),
+          x, x_dtype, x_ld, B, T, F, Cin, w, bias, ntaps, taps, Cout, lens, y_raw, y_raw_dtype, y_raw_ld, y_act,
+          y_act_dtype, y_act_ld, act, slope, al16(y_raw, y_raw_ld, y_raw_dtype) ? 1 : 0, al16(y_act, y_act_ld, y_act_dtype) ? 1 : 0));
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
@@ -1171,6 +1515,12 @@ extern "C" int as_dwconv(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B
     ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
+  if (!glu && vec8_ok(x, x_dtype, x_ld, out, out_dtype, out_ld, C, total) && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    ASB_CUDA(launch_k(dwconv_vec8_kernel, ew_grid(total / 8), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, w, bias, kt, kf, st, sf,
+                      pt, pf, To, Fo, lens_in, lens_out, act, slope, out, out_dtype, out_ld));
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
   ASB_CUDA(launch_k(dwconv_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, glu, w, bias, kt, kf, st, sf,
                                                        pt, pf, To, Fo, lens_in, lens_out, act, slope, out,
                                                        out_dtype, out_ld));
@@ -1185,6 +1535,12 @@ extern "C" int as_avgpool(const void* x, int32_t x_dtype, int64_t x_ld, int32_t 
   const int To = (T + pt - 1) / pt, Fo = F / pf;
   const long long total = (long long)B * To * Fo * C;
   if (total == 0) return AS_OK;
+  if (vec8_ok(x, x_dtype, x_ld, out, out_dtype, out_ld, C, total)) {
+    ASB_CUDA(launch_k(avgpool_vec8_kernel, ew_grid(total / 8), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, pt, pf, To, Fo, out, out_dtype,
+                      out_ld));
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
   ASB_CUDA(launch_k(avgpool_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, pt, pf, To, Fo, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
@@ -1198,6 +1554,12 @@ extern "C" int as_affine_act_maxpool(const void* x, int32_t x_dtype, int64_t x_l
   const int Fo = F / pf;
   const long long total = (long long)B * T * Fo * C;
   if (total == 0) return AS_OK;
+  if (vec8_ok(x, x_dtype, x_ld, out, out_dtype, out_ld, C, total)) {
+    ASB_CUDA(launch_k(affine_act_maxpool_vec8_kernel, ew_grid(total / 8), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, scale, shift,
+                      slope, pf, Fo, out, out_dtype, out_ld));
+    ASB_CUDA(cudaGetLastError());
+    return AS_OK;
+  }
   ASB_CUDA(launch_k(affine_act_maxpool_kernel, ew_grid(total), 256, 0, ST(stream), x, x_dtype, x_ld, B, T, F, C, scale, shift,
                                                                    slope, pf, Fo, out, out_dtype, out_ld));
   ASB_CUDA(cudaGetLastError());

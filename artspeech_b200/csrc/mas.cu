@@ -40,7 +40,8 @@ template <int R>
 __global__ void __launch_bounds__(256)
 mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
            const int32_t* __restrict__ y_len, float* __restrict__ path, int Tx, int Ty,
-           int tie_move, uint32_t* __restrict__ dir_ws, int dir_in_smem, int cw, int NW) {
+           int tie_move, uint32_t* __restrict__ dir_ws, int dir_in_smem, int cw, int NW,
+           int32_t* __restrict__ dur, int32_t* __restrict__ tok) {
   pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   constexpr int WR = 32 * R;       // rows per warp
   constexpr int PX = WR + 1;       // odd pitch of a warp's transposed [col][row] sub-tile
@@ -66,6 +67,9 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
   const int nsteps = nblk > 0 ? nblk + NW - 1 : 0;
 
   const size_t total = (size_t)Tx * Ty;
+  // optional alignment outputs (as_mas_align): durations = row sums of the path, tok = row of every column
+  if (dur) for (int i = tid; i < Tx; i += nthr) dur[(size_t)b * Tx + i] = 0;
+  if (tok) for (int i = tid; i < Ty; i += nthr) tok[(size_t)b * Ty + i] = -1;
   if (nblk == 0 || xl == 0) {
     // empty item (x_len == 0 or y_len == 0): the path is all zeros
     for (size_t i = tid; i < total; i += nthr) pb[i] = 0.f;
@@ -226,7 +230,11 @@ mas_kernel(const float* __restrict__ value, const int32_t* __restrict__ x_len,
         if (y >= 1) r += (m[cc] >> r) & 1u;  // transition y -> y-1
       }
     }
-    if (lane <= hi && myrow >= 0) pb[(size_t)myrow * Ty + (w << 5) + lane] = 1.0f;
+    if (lane <= hi && myrow >= 0) {
+      pb[(size_t)myrow * Ty + (w << 5) + lane] = 1.0f;
+      if (tok) tok[(size_t)b * Ty + (w << 5) + lane] = myrow;
+      if (dur) atomicAdd(&dur[(size_t)b * Tx + myrow], 1);
+    }
     idx0 -= r;
   }
 }
@@ -256,10 +264,11 @@ static bool mas_plan(int Tx, int Ty, MasPlan& p) {
 
 template <int R>
 static int launch_mas(const MasPlan& p, const float* value, const int32_t* x_len, const int32_t* y_len,
-                      float* path, int B, int Tx, int Ty, int tie_mode, void* ws, cudaStream_t st) {
+                      float* path, int B, int Tx, int Ty, int tie_mode, void* ws, cudaStream_t st,
+                      int32_t* dur = nullptr, int32_t* tok = nullptr) {
   ASB_CUDA(cudaFuncSetAttribute(mas_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   ASB_CUDA(launch_k(mas_kernel<R>, B, 32 * p.NW, p.smem, st, value, x_len, y_len, path, Tx, Ty, tie_mode,
-                                              reinterpret_cast<uint32_t*>(ws), p.dir_in_smem, p.cw, p.NW));
+                                              reinterpret_cast<uint32_t*>(ws), p.dir_in_smem, p.cw, p.NW, dur, tok));
   ASB_CUDA(cudaGetLastError());
   return AS_OK;
 }
@@ -273,26 +282,41 @@ extern "C" size_t as_mas_workspace_bytes(int32_t B, int32_t Tx, int32_t Ty) {
   return p.dir_in_smem ? 0 : (size_t)B * p.dir_bytes_per_item;
 }
 
+static int mas_run(const char* who, const float* value, const int32_t* x_len, const int32_t* y_len, float* path, int32_t B,
+                   int32_t Tx, int32_t Ty, int32_t tie_mode, void* workspace, size_t workspace_bytes, void* stream,
+                   int32_t* dur, int32_t* tok) {
+  using namespace asb;
+  if (B == 0 || Tx == 0 || Ty == 0) return AS_OK;
+  ASB_REQUIRE(B > 0 && Tx > 0 && Ty > 0, AS_ERR_SHAPE, "%s: bad shape", who);
+  ASB_REQUIRE(value && x_len && y_len && path, AS_ERR_SHAPE, "%s: null pointer", who);
+  ASB_REQUIRE(tie_mode == 0 || tie_mode == 1, AS_ERR_SHAPE, "%s: tie_mode", who);
+  int rc = check_arch();
+  if (rc != AS_OK) return rc;
+  MasPlan p;
+  ASB_REQUIRE(mas_plan(Tx, Ty, p), AS_ERR_SHAPE, "%s: Tx=%d exceeds the supported maximum of 1280", who, Tx);
+  if (!p.dir_in_smem) {
+    ASB_REQUIRE(workspace != nullptr && workspace_bytes >= p.dir_bytes_per_item * (size_t)B, AS_ERR_WORKSPACE,
+                "%s: workspace too small (%zu < %zu)", who, workspace_bytes, p.dir_bytes_per_item * (size_t)B);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.R == 1) return launch_mas<1>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st, dur, tok);
+  if (p.R == 3) return launch_mas<3>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st, dur, tok);
+  return launch_mas<5>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st, dur, tok);
+}
+
 extern "C" int as_mas_maximum_path(const float* value, const int32_t* x_len, const int32_t* y_len,
                                    float* path, int32_t B, int32_t Tx, int32_t Ty,
                                    int32_t tie_mode, void* workspace, size_t workspace_bytes,
                                    void* stream) {
-  using namespace asb;
-  if (B == 0 || Tx == 0 || Ty == 0) return AS_OK;
-  ASB_REQUIRE(B > 0 && Tx > 0 && Ty > 0, AS_ERR_SHAPE, "as_mas_maximum_path: bad shape");
-  ASB_REQUIRE(value && x_len && y_len && path, AS_ERR_SHAPE, "as_mas_maximum_path: null pointer");
-  ASB_REQUIRE(tie_mode == 0 || tie_mode == 1, AS_ERR_SHAPE, "as_mas_maximum_path: tie_mode");
-  int rc = check_arch();
-  if (rc != AS_OK) return rc;
-  MasPlan p;
-  ASB_REQUIRE(mas_plan(Tx, Ty, p), AS_ERR_SHAPE, "as_mas_maximum_path: Tx=%d exceeds the supported maximum of 1280", Tx);
-  if (!p.dir_in_smem) {
-    ASB_REQUIRE(workspace != nullptr && workspace_bytes >= p.dir_bytes_per_item * (size_t)B, AS_ERR_WORKSPACE,
-                "as_mas_maximum_path: workspace too small (%zu < %zu)", workspace_bytes,
-                p.dir_bytes_per_item * (size_t)B);
-  }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.R == 1) return launch_mas<1>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st);
-  if (p.R == 3) return launch_mas<3>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st);
-  return launch_mas<5>(p, value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, st);
+  return mas_run("as_mas_maximum_path", value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, workspace_bytes, stream,
+                 nullptr, nullptr);
+}
+
+extern "C" int as_mas_align(const float* value, const int32_t* x_len, const int32_t* y_len, float* path,
+                            int32_t* durations, int32_t* token_of_frame, int32_t B, int32_t Tx, int32_t Ty,
+                            int32_t tie_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B > 0 && Tx > 0 && Ty > 0)
+    ASB_REQUIRE(durations && token_of_frame, AS_ERR_SHAPE, "as_mas_align: null pointer");
+  return mas_run("as_mas_align", value, x_len, y_len, path, B, Tx, Ty, tie_mode, workspace, workspace_bytes, stream,
+                 durations, token_of_frame);
 }

@@ -26,10 +26,14 @@ class Synthesizer:
     with its own CUDA-graph instance and buffers, so the latency-bound acoustic model of one batch
     overlaps the throughput-bound vocoder of the previous one.  The outputs of a pipelined call are
     produced on ``last_stream``: consume them there (``with torch.cuda.stream(syn.last_stream)``) or
-    after ``join()``, which makes the current stream wait for every call issued so far."""
+    after ``join()``, which makes the current stream wait for every call issued so far.
+    ``pcm16=True`` returns int16 samples (``rint(32767 * wav)``, the on-disk format of ``soundfile.write`` at
+    test.py:119) written directly by the vocoder's last kernel: half the device->host bytes per utterance."""
 
-    def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True, pipeline_depth: int = 1):
+    def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True, pipeline_depth: int = 1,
+                 pcm16: bool = False):
         self.device = torch.device(device)
+        self.pcm16 = bool(pcm16)
         self.pipeline_depth = max(1, int(pipeline_depth))
         self._slot_streams = None
         self._slot_done = {}
@@ -55,7 +59,7 @@ class Synthesizer:
     def _forward(self, tokens, tok_lens, mels, mel_lens, durations, host_meta=None, voice=None):
         mel, aux = self.model([tokens, tok_lens, mels, mel_lens], step="test", durations=durations, return_aux=True,
                               host_meta=host_meta, voice=voice)
-        wav = self.generator(mel, aux["mel_lengths"])
+        wav = self.generator(mel, aux["mel_lengths"], pcm16=self.pcm16)
         return wav.view(wav.shape[0], -1), aux["mel_lengths"], mel
 
     @torch.no_grad()

@@ -60,6 +60,62 @@ def maximum_path_lens(value: torch.Tensor, x_len: torch.Tensor, y_len: torch.Ten
     return path if dtype == torch.float32 else path.to(dtype)
 
 
+@torch.no_grad()
+def align_lens(value: torch.Tensor, x_len: torch.Tensor, y_len: torch.Tensor, tie_mode: int = TIE_STAY):
+    """MAS plus what its training callers derive from the path, from ONE kernel launch
+    (train_second.py:181-187, train_first.py:176-181): returns ``(path, durations, token_of_frame)`` with
+    ``durations[B,Tx] int32 == path.sum(-1)`` (``d_gt``) and ``token_of_frame[B,Ty] int32`` = the row the path
+    occupies in each column (-1 for ``y >= y_len``)."""
+    if not value.is_cuda:
+        raise _lib.AsError("artspeech_b200.mas requires CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    v = value.detach()
+    if v.dtype != torch.float32:
+        v = v.float()
+    v = v.contiguous()
+    B, Tx, Ty = v.shape
+    xl = x_len.to(device=v.device, dtype=torch.int32).contiguous()
+    yl = y_len.to(device=v.device, dtype=torch.int32).contiguous()
+    path = torch.empty_like(v)
+    dur = torch.empty(B, Tx, dtype=torch.int32, device=v.device)
+    tok = torch.empty(B, Ty, dtype=torch.int32, device=v.device)
+    ws_bytes = lib.as_mas_workspace_bytes(B, Tx, Ty)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=v.device)
+    stream = torch.cuda.current_stream(v.device).cuda_stream
+    with torch.cuda.device(v.device):
+        rc = lib.as_mas_align(v.data_ptr(), xl.data_ptr(), yl.data_ptr(), path.data_ptr(), dur.data_ptr(),
+                              tok.data_ptr(), B, Tx, Ty, int(tie_mode), ws.data_ptr(), ws_bytes, stream)
+    _lib.check(rc, "as_mas_align")
+    return path, dur, tok
+
+
+@torch.no_grad()
+def expand_tokens(x: torch.Tensor, token_of_frame: torch.Tensor) -> torch.Tensor:
+    """``x[B,C,Tx] @ path[B,Tx,Ty]`` for the 0/1 path that ``token_of_frame`` describes, as a gather
+    (models.py:296,323-324: ``T_en @ s2s_attn_mono``, ``A_en @ s2s_attn_mono``).  Bit-identical to the fp32
+    matmul: every output is one input value (or 0 past ``y_len``)."""
+    if not x.is_cuda:
+        raise _lib.AsError("artspeech_b200.mas requires CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    xf = x.detach().float().contiguous()
+    B, C, Tx = xf.shape
+    tok = token_of_frame.to(device=xf.device, dtype=torch.int32).contiguous()
+    Ty = tok.shape[1]
+    out = torch.empty(B, C, Ty, dtype=torch.float32, device=xf.device)
+    stream = torch.cuda.current_stream(xf.device).cuda_stream
+    with torch.cuda.device(xf.device):
+        rc = lib.as_expand_tokens(xf.data_ptr(), tok.data_ptr(), out.data_ptr(), B, C, Tx, Ty, stream)
+    _lib.check(rc, "as_expand_tokens")
+    return out.to(x.dtype)
+
+
+@torch.no_grad()
+def align(value: torch.Tensor, mask: torch.Tensor, tie_mode: int = TIE_STAY):
+    """``align_lens`` on the reference's mask argument (``mask_from_lens(...)``, S_monotonic_align.py:117-133)."""
+    x_len, y_len = _lens_from_mask(mask)
+    return align_lens(value, x_len, y_len, tie_mode)
+
+
 def _lens_from_mask(mask: torch.Tensor):
     # x_len = mask[:, :, 0].sum(1), y_len = mask[:, 0, :].sum(1) (S_monotonic_align.py:14-15)
     m = mask != 0

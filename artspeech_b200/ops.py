@@ -16,9 +16,10 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_ABS, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SWISH, ACT_TANH, AS_BF16, AS_F16,
-                   AS_F32)
+                   AS_F32, AS_PCM16)
 
-_DT = {torch.float16: AS_F16, torch.bfloat16: AS_BF16, torch.float32: AS_F32}
+# torch.int16 = 16-bit PCM, accepted as the activated output of a single-output-channel convolution only
+_DT = {torch.float16: AS_F16, torch.bfloat16: AS_BF16, torch.float32: AS_F32, torch.int16: AS_PCM16}
 
 # number of kernels of ours launched since the last reset (bench.py reports it as gpu_launches)
 launch_count = 0

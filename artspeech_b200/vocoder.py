@@ -163,18 +163,54 @@ class Generator(nn.Module):
 
     # -- forward ----------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``x``: mel ``[B, num_mels, T]`` -> waveform ``[B, 1, T*prod(upsample_rates)]`` (fp32)."""
+    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None, pcm16: bool = False) -> torch.Tensor:
+        """``x``: mel ``[B, num_mels, T]`` -> waveform ``[B, 1, T*prod(upsample_rates)]`` (fp32).
+        ``pcm16=True`` (extension): int16 samples ``rint(32767 * wav)`` straight from the conv_post kernel -- the
+        samples ``soundfile.write(path, wav, 24000)`` (test.py:119) stores -- halving the device->host bytes."""
         mel_cl = x.detach().transpose(1, 2).to(self.compute_dtype).contiguous()   # [B, T, 80]
         if lengths is not None:  # frames beyond an utterance's length must not leak into it
             keep = torch.arange(mel_cl.shape[1], device=mel_cl.device)[None, :] < lengths.to(mel_cl.device)[:, None]
             mel_cl = mel_cl * keep.unsqueeze(-1).to(mel_cl.dtype)
-        wav = self.forward_channels_last(mel_cl, lengths)
+        wav = self.forward_channels_last(mel_cl, lengths, torch.int16 if pcm16 else torch.float32)
         return wav.view(wav.shape[0], 1, -1)
 
+    def receptive_field_frames(self) -> int:
+        """Mel frames on either side that can influence an output sample: conv_pre (k 7) + per stage the
+        ConvTranspose1d reach and the widest MRF branch ``sum_d (k-1)/2 * (d + 1)`` at that stage's rate +
+        conv_post (k 7), rounded up (Vocoder/vocoder.py:11-48,75-116).  14 for the V1 config."""
+        import math
+        rf, rate = 3.0, 1
+        for i, (u, k) in enumerate(zip(self.h.upsample_rates, self.h.upsample_kernel_sizes)):
+            rf += math.ceil((k - u) / 2 / u + 1) / rate       # input positions a transposed-conv output reaches
+            rate *= u
+            widest = max(sum((kk - 1) // 2 * (d + 1) for d in ds)
+                         for kk, ds in zip(self.h.resblock_kernel_sizes, self.h.resblock_dilation_sizes))
+            rf += widest / rate
+        rf += 3.0 / rate
+        return int(math.ceil(rf))
+
     @torch.no_grad()
-    def forward_channels_last(self, mel_cl: torch.Tensor, lengths: Optional[torch.Tensor] = None):
-        """``mel_cl``: ``[B, T, 80]`` in the compute dtype.  Returns ``[B, T*300]`` fp32."""
+    def stream(self, x: torch.Tensor, chunk_frames: int = 64, halo_frames: Optional[int] = None, pcm16: bool = False):
+        """Chunked vocoding for latency-bound serving: yields ``(first_sample, wav_chunk)`` with
+        ``wav_chunk`` ``[B, 1, <=chunk_frames*hop]``.  Every chunk is vocoded with ``halo_frames`` (default: the
+        receptive field) of real context on both sides and only its centre is kept, so the concatenation equals
+        ``forward(x)``; the first audio is available after one ``chunk_frames + halo`` pass instead of the whole
+        utterance."""
+        halo = self.receptive_field_frames() if halo_frames is None else int(halo_frames)
+        hop = 1
+        for u in self.h.upsample_rates:
+            hop *= u
+        T = x.shape[2]
+        for t0 in range(0, T, chunk_frames):
+            t1 = min(T, t0 + chunk_frames)
+            a, b = max(0, t0 - halo), min(T, t1 + halo)
+            wav = self.forward(x[:, :, a:b], pcm16=pcm16)
+            yield t0 * hop, wav[:, :, (t0 - a) * hop:(t1 - a) * hop]
+
+    @torch.no_grad()
+    def forward_channels_last(self, mel_cl: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                              out_dtype: torch.dtype = torch.float32):
+        """``mel_cl``: ``[B, T, 80]`` in the compute dtype.  Returns ``[B, T*300]`` fp32 (or int16 PCM)."""
         dev = mel_cl.device
         if self._plan is None:
             self._plan = self._build_plan(dev)
@@ -244,5 +280,5 @@ class Generator(nn.Module):
                         # last branch: (xs + branch) / num_kernels, then the next stage's LeakyReLU
                         _, a = ops.conv(t, c2s[m], res1=r, res2=xs, scale=1.0 / self.num_kernels,
                                         act_out=dt, act=ops.ACT_LRELU, slope=next_slope, lens=lens)
-        _, wav = ops.conv(a, plan["post"], act_out=torch.float32, act=ops.ACT_TANH, lens=lens)
+        _, wav = ops.conv(a, plan["post"], act_out=out_dtype, act=ops.ACT_TANH, lens=lens)
         return wav.view(B, L)

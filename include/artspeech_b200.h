@@ -34,7 +34,10 @@ typedef enum as_status {
   AS_ERR_WORKSPACE = -6
 } as_status;
 
-typedef enum as_dtype { AS_F16 = 0, AS_BF16 = 1, AS_F32 = 2 } as_dtype;
+/* AS_PCM16: output-only, accepted as y_act_dtype of a single-output-channel 1-D convolution (the vocoder's
+ * conv_post + tanh, Vocoder/vocoder.py:113-115): int16 = rint(32767 * y), what soundfile.write(path, wav, 24000)
+ * (test.py:119) stores for a float waveform. */
+typedef enum as_dtype { AS_F16 = 0, AS_BF16 = 1, AS_F32 = 2, AS_PCM16 = 3 } as_dtype;
 
 typedef enum as_act {
   AS_ACT_NONE = 0,
@@ -60,6 +63,21 @@ size_t as_mas_workspace_bytes(int32_t B, int32_t Tx, int32_t Ty);
 int as_mas_maximum_path(const float* value, const int32_t* x_len, const int32_t* y_len,
                         float* path, int32_t B, int32_t Tx, int32_t Ty, int32_t tie_mode,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* MAS plus the two reductions its training callers take of the path (train_second.py:181-187,
+ * train_first.py:176-181, models.py:296,323-324), produced by the same back-track:
+ *   durations      [B, Tx] int32 = path.sum(-1)                 (d_gt, train_second.py:182)
+ *   token_of_frame [B, Ty] int32 = row of the path in column y, -1 for y >= y_len
+ * so that `T_en @ s2s_attn_mono` becomes the gather as_expand_tokens below. */
+int as_mas_align(const float* value, const int32_t* x_len, const int32_t* y_len, float* path,
+                 int32_t* durations, int32_t* token_of_frame, int32_t B, int32_t Tx, int32_t Ty,
+                 int32_t tie_mode, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[b, c, y] = x[b, c, token_of_frame[b, y]] (0 where token_of_frame < 0): bit-identical to
+ * `x @ path` for a 0/1 path with one 1 per column (models.py:296,323-324).  x [B, C, Tx] fp32
+ * (reference layout, Tx contiguous), out [B, C, Ty] fp32. */
+int as_expand_tokens(const float* x, const int32_t* token_of_frame, float* out, int32_t B, int32_t C,
+                     int32_t Tx, int32_t Ty, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

@@ -68,6 +68,33 @@ def test_mas_edge_cases():
     assert torch.equal(out[2, :, :7], torch.eye(7)) and out[2, :, 7:].sum() == 0   # x_len == y_len: diagonal
 
 
+@pytest.mark.parametrize("shape", [(5, 37, 90), (8, 200, 1000), (3, 300, 1400)])
+def test_mas_align_training_chain(shape):
+    """The chain MAS sits in at train_second.py:178-187 / models.py:323-324: softmax -> mask_from_lens ->
+    maximum_path -> d_gt = path.sum(-1) and T_en @ path.  as_mas_align returns path, durations and the
+    frame -> token map from one launch; as_expand_tokens replaces the dense matmul.  All bit-exact."""
+    B, Tx, Ty = shape
+    rng = np.random.default_rng(11)
+    feat = torch.from_numpy(rng.standard_normal((B, Tx, Ty)).astype(np.float32) * 3.0)
+    attn = torch.softmax(feat, dim=-1)
+    xl = rng.integers(max(1, Tx // 2), Tx + 1, B); yl = np.maximum(rng.integers(Ty // 2, Ty + 1, B), xl)
+    xl[0], yl[0] = Tx, Ty
+    xlt, ylt = torch.from_numpy(xl).to(DEV), torch.from_numpy(yl).to(DEV)
+    mask = mas.mask_from_lens(attn.to(DEV), xlt, ylt)
+    path, dur, tok = mas.align(attn.to(DEV), mask)
+    ref = mas_oracle.maximum_path(attn.numpy(), xl, yl, "stay")
+    assert np.array_equal(path.cpu().numpy(), ref)
+    assert np.array_equal(dur.cpu().numpy(), ref.sum(-1).astype(np.int32))           # d_gt
+    tok_ref = np.where(np.arange(Ty)[None, :] < yl[:, None], ref.argmax(1), -1)
+    assert np.array_equal(tok.cpu().numpy(), tok_ref)
+    T_en = torch.from_numpy(rng.standard_normal((B, 64, Tx)).astype(np.float32))
+    want = T_en @ torch.from_numpy(ref)                                               # models.py:323
+    got = mas.expand_tokens(T_en.to(DEV), tok).cpu()
+    assert torch.equal(got, want)
+    # the plain entry point still agrees (shared kernel, null outputs)
+    assert torch.equal(mas.maximum_path(attn.to(DEV), mask), path)
+
+
 def test_vocoder_vs_reference_golden():
     g = util.load_golden("vocoder_small.pt")
     gen = util.generator(g["checkpoint_seed"]).to(DEV)
@@ -81,6 +108,21 @@ def test_vocoder_vs_reference_golden():
     one = restate.generator_forward(util.generator(g["checkpoint_seed"]).cpu().state_dict(), g["mel"][1:2, :, :11])
     assert util.snr_db(wav_r[1:2, :, :11 * 300], one) >= util.WAV_SNR_DB
     assert wav_r[1, :, 11 * 300:].abs().max().item() == 0.0
+    # 16-bit PCM straight from the conv_post kernel == what soundfile.write stores for the float waveform
+    # (test.py:119; libsndfile: lrint(32767 * x)), and still >= 35 dB against the reference waveform
+    pcm = gen(g["mel"].to(DEV), pcm16=True).cpu()
+    assert pcm.dtype == torch.int16 and pcm.shape == wav.shape
+    assert torch.equal(pcm, torch.round(wav * 32767.0).clamp(-32768, 32767).to(torch.int16))
+    assert util.snr_db(pcm.float() / 32767.0, g["wav"]) >= util.WAV_SNR_DB
+    # chunked vocoding with a receptive-field halo reproduces the one-shot pass
+    mel = g["mel"].to(DEV)
+    parts = list(gen.stream(mel, chunk_frames=8))
+    assert [p[0] for p in parts] == [i * 8 * 300 for i in range(len(parts))]
+    cat = torch.cat([p[1] for p in parts], dim=2).cpu()
+    assert cat.shape == wav.shape and util.snr_db(cat, wav) >= 60.0
+    with pytest.raises(Exception):      # PCM is only defined for the single-channel output convolution
+        from artspeech_b200 import ops
+        ops.conv(torch.zeros(1, 128, 64, device=DEV, dtype=torch.bfloat16), gen._plan["ups"][3], act_out=torch.int16)
     util._MODELS.clear()
 
 

@@ -27,6 +27,24 @@ def test_mas_tie_modes_differ_on_ties():
     assert diff >= 1   # v1 and v2 disagree on tie-heavy inputs
 
 
+def test_vocoder_receptive_field_bounds_the_reference():
+    """Generator.receptive_field_frames() (the halo of the chunked `stream`) checked on the reference restatement:
+    a chunk vocoded with that much real context on both sides reproduces the full pass in its centre; one frame of
+    context does not."""
+    gen = util.generator(0)
+    sd = gen.state_dict()
+    torch.manual_seed(5)
+    mel = torch.randn(1, 80, 72).clamp(-2, 2)
+    full = restate.generator_forward(sd, mel)
+    halo = gen.receptive_field_frames()
+    assert 10 <= halo <= 16
+    t0, t1 = 30, 40
+    part = restate.generator_forward(sd, mel[:, :, t0 - halo:t1 + halo])[:, :, halo * 300:(halo + t1 - t0) * 300]
+    assert (part - full[:, :, t0 * 300:t1 * 300]).abs().max().item() < 1e-6
+    short = restate.generator_forward(sd, mel[:, :, t0 - 1:t1 + 1])[:, :, 300:(1 + t1 - t0) * 300]
+    assert (short - full[:, :, t0 * 300:t1 * 300]).abs().max().item() > 1e-4
+
+
 def test_vocoder_restatement_and_host_logic(sim):
     g = util.load_golden("vocoder_small.pt")
     gen = util.generator(g["checkpoint_seed"])

@@ -227,9 +227,12 @@ def test_instnorm_adain(up):
 
 
 @pytest.mark.parametrize("up", [False, True])
-@pytest.mark.parametrize("shape", [(3, 100, 96), (2, 801, 512), (1, 1600, 64)])
+@pytest.mark.parametrize("shape", [(3, 100, 96), (2, 801, 512), (1, 1600, 64), (24, 200, 1024), (10, 800, 1216), (2, 1700, 256),
+                                   (4, 300, 384)])
 def test_adain_norm_fused(shape, up):
-    """as_adain_norm_apply (single pass, slab in shared memory; T > 1536 takes the two-pass path)."""
+    """as_adain_norm_apply (single pass, slab in shared memory; C < 128 takes the 32-channel TMA / cluster
+    kernels; C >= 128 the wide-row cluster kernel with 1, 2, 4 or 8 CTAs per cluster depending on T, including a
+    partial last 128-channel group (C = 1216) and the halo row of the upsampling variant)."""
     B, T, C = shape
     torch.manual_seed(3)
     x = torch.randn(B, T, C) * 0.7 + torch.randn(C) * 30.0       # bias-dominated channels (|mean| >> std)
@@ -295,6 +298,15 @@ def test_conv_small_dwconv_pools():
     ref = sim.affine_act_maxpool(y, scale, shift, 0.01, 2, torch.float16)
     out = ops.affine_act_maxpool(y.to(DEV), scale.to(DEV), shift.to(DEV), 0.01, 2, torch.float16)
     _close(out, ref, 2e-3, "maxpool")
+    # fp32 tensors / odd channel counts take the scalar kernels (the fp16 cases above take the 8-channel ones)
+    yf = torch.randn(2, 21, 10, 12)
+    wd, bd = torch.randn(9, 12), torch.randn(12)
+    _close(ops.dwconv(yf.to(DEV), wd.to(DEV), bd.to(DEV), (3, 3), (2, 2), (1, 1), out_dtype=torch.float32),
+           sim.dwconv(yf, wd, bd, (3, 3), (2, 2), (1, 1), out_dtype=torch.float32), 1e-5, "dwconv fp32")
+    _close(ops.avgpool(yf.to(DEV), 2, 2, torch.float32), sim.avgpool(yf, 2, 2, torch.float32), 1e-5, "avgpool fp32")
+    sc12, sh12 = torch.rand(12) + 0.5, torch.randn(12)
+    _close(ops.affine_act_maxpool(yf.to(DEV), sc12.to(DEV), sh12.to(DEV), 0.01, 2, torch.float32),
+           sim.affine_act_maxpool(yf, sc12, sh12, 0.01, 2, torch.float32), 1e-5, "maxpool fp32")
     for ts in (1, 2):
         ref = sim.global_avgpool(y, 0.2, torch.float32, ts)
         out = ops.global_avgpool(y.to(DEV), 0.2, torch.float32, ts)

@@ -41,5 +41,6 @@ def run(B, T, C, xdt, up=False, reps=5, nset=6):
 if __name__ == "__main__":
     for C in (512, 1024, 1216):
         run(16, 800, C, torch.float32)
+    run(512, 800, 32, torch.float32)      # same bytes as 16x800x1024 but every CTA's slab is contiguous (DRAM-page experiment)
     run(16, 400, 512, torch.float32, up=True)
     run(16, 1600, 512, torch.float32)     # long path (stats + apply)

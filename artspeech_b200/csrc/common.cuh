@@ -89,8 +89,13 @@ __device__ __forceinline__ float from16(uint16_t u, int dtype) {
   if (dtype == AS_F16) return __half2float(__ushort_as_half(u));
   return __bfloat162float(__ushort_as_bfloat16(u));
 }
-__device__ __forceinline__ uint32_t pack16(float a, float b, int dtype) {
-  return uint32_t(to16(a, dtype)) | (uint32_t(to16(b, dtype)) << 16);
+__device__ __forceinline__ uint32_t pack16(float a, float b, int dtype) {   // one F2FP.PACK_AB: a -> low half, b -> high half
+  if (dtype == AS_F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 // generic element load: dtype in {AS_F16, AS_BF16, AS_F32}
 __device__ __forceinline__ float ldany(const void* p, int64_t i, int dtype) {

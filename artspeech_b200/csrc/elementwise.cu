@@ -502,135 +502,182 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
   }
 }
 
-// Wide-row cluster variant (the one the decoder's shapes take).  The 32-channel slabs above make every CTA read
-// 128-byte pieces 4 KB apart: DRAM pages are opened for 128 bytes at a time and the pass saturates near 2.9 TB/s
-// whatever the CTA-level overlap is (a persistent multi-stage ring of the same slabs measured no faster).  Here a
-// thread-block CLUSTER of CS CTAs owns 128 channels of one item -- 512 contiguous bytes per row -- and splits the
-// frames: CTA r keeps rows [r*TR, (r+1)*TR) in shared memory (one or two TMA boxes), partial sums / squared
-// deviations are exchanged through distributed shared memory around two cluster barriers (exact two-pass
-// statistics), and every warp instruction then writes one 256-byte row segment of the 16-bit output.
-constexpr int ADW_CW = 128;               // channels per cluster
-constexpr int ADW_SLAB_BYTES = 110 * 1024;
+// Persistent ring variant (the one the decoder's shapes take).  ncu on the kernel above: DRAM is busy 19 % of the
+// time -- the pass is bound by INSTRUCTION ISSUE, not memory (about 29 instructions per element over three
+// shared-memory passes, block-wide reductions in every thread, loads / statistics / stores of the resident CTAs in
+// lockstep); neither a contiguous-slab layout, nor 512-byte rows split over a cluster, nor cp.async instead of TMA
+// changed the 2.6-2.9 TB/s.  This version (a) makes ONE persistent CTA per SM walk the (item, 32-channel slab)
+// units through an S-stage shared-memory ring fed by TMA, so the copies of units k+1 .. k+S-1 cost no instructions
+// and are in flight while unit k is processed, and (b) cuts the arithmetic to two passes: one statistics pass
+// (sums of d = x - pivot and d^2, pivot = the channel's first frame, so no digits are lost on bias-dominated
+// channels), a 64-thread fold of the warps' partials, and one fused-multiply-add + max + pack + 8-byte store per
+// four elements.
+constexpr int ADR_THREADS = 512;
+constexpr int ADR_WARPS = ADR_THREADS / 32;
+constexpr int ADR_ROWS = ADR_WARPS * 4;   // rows covered per pass iteration
+constexpr int ADR_MAX_STAGES = 4;
 
-__device__ __forceinline__ float4 adw_ld_peer4(const float* p, uint32_t rank) {
-  uint32_t ra;
-  float4 v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
-  return v;
-}
-
-template <bool UP, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(256)
-adain_wide_kernel(const __grid_constant__ CUtensorMap tmx, int T, int TR, int BR, int nbox, int C,
+template <bool UP>
+__global__ void __launch_bounds__(ADR_THREADS, 1)
+adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbox, int C, int nslab, int units, int S,
                   const float* __restrict__ gb, long long gb_ld, float eps, float slope,
                   const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
                   void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
   extern __shared__ __align__(128) float slab_raw[];
-  __shared__ __align__(16) float red[8][ADW_CW];
-  __shared__ __align__(16) float part[2][ADW_CW];          // this CTA's partial sum / partial squared deviation
-  __shared__ __align__(8) unsigned long long bar_storage;
-  float* slab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(slab_raw) + 127) & ~uintptr_t(127));   // [nbox*BR][128]
-  const uint32_t bar = smem_u32(&bar_storage);
+  __shared__ __align__(16) float red[2][ADR_WARPS][32];     // per-warp partial sums / squared sums
+  __shared__ __align__(16) float tot[2][32];
+  __shared__ __align__(8) unsigned long long bars[ADR_MAX_STAGES];
+  float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(slab_raw) + 127) & ~uintptr_t(127));   // [S][nbox*BR][32]
+  const uint32_t slab_bytes = (uint32_t)nbox * BR * 128u;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t rank = CS == 1 ? 0u : adf_cluster_rank();
-  const int b = blockIdx.y, cb = (blockIdx.x / CS) * ADW_CW, c = cb + 4 * lane;
-  const bool cok = c < C;                                   // C % 4 == 0: a quad is all-in or all-out
-  const int len = lens ? min(lens[b], T) : T;
-  const int t_lo = (int)rank * TR;
+  const int r4 = lane >> 3, c4 = lane & 7;
+  const int row0 = w * 4 + r4;
+  auto issue = [&](int u, int stage) {                      // one thread: nbox bulk tensor copies, rows >= T / channels >= C arrive as zeros
+    const uint32_t bar = smem_u32(&bars[stage]);
+    const uint32_t dst = smem_u32(ring) + (uint32_t)stage * slab_bytes;
+    const int b = u / nslab, cb = (u - b * nslab) * 32;
+    mbar_expect_tx(bar, slab_bytes);
+    for (int k = 0; k < nbox; ++k) tma_load_3d(dst + (uint32_t)k * BR * 128u, &tmx, bar, cb, k * BR, b);
+  };
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&bars[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)nbox * BR * (ADW_CW * 4u));
-    for (int k = 0; k < nbox; ++k) tma_load_3d(smem_u32(slab) + (uint32_t)k * BR * (ADW_CW * 4u), &tmx, bar, cb, t_lo + k * BR, b);
+    for (int s = 0; s < S; ++s) {
+      const int u = blockIdx.x + s * gridDim.x;
+      if (u < units) issue(u, s);
+    }
   }
   __syncthreads();
-  mbar_wait(bar, 0);
-  const int nv = max(0, min(len - t_lo, TR));               // rows of this CTA that enter the statistics
-  auto cluster_total = [&](float4 p, int which) -> float4 {
-    *reinterpret_cast<float4*>(&red[w][4 * lane]) = p;
-    __syncthreads();
-    if (w == 0) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 q = *reinterpret_cast<const float4*>(&red[i][4 * lane]);
-        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
-      }
-      *reinterpret_cast<float4*>(&part[which][4 * lane]) = t;
+  int stage = 0;
+  uint32_t phase = 0;
+  const bool mx = slope >= 0.f && slope <= 1.f;            // LeakyReLU(y) = max(y, slope * y)
+  // per-unit scalars (length, gamma, beta) are fetched one unit ahead with volatile loads: issued at the top of unit
+  // k for unit k + 1, consumed a whole unit later, so their L2 / DRAM latency never stalls the in-order pipeline
+  // (ncu: with the loads next to their use, 30 % of the samples sat on the first instruction that reads gamma)
+  auto load_scalars = [&](int u, int& len_o, float4& g_o, float4& be_o) {
+    const int b = u / nslab, c = (u - b * nslab) * 32 + 4 * c4;
+    len_o = T;
+    if (lens) { asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(len_o) : "l"(lens + b)); }
+    if (c < C) {
+      const float* gp = gb + (long long)b * gb_ld + c;
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g_o.x), "=f"(g_o.y), "=f"(g_o.z), "=f"(g_o.w) : "l"(gp));
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(be_o.x), "=f"(be_o.y), "=f"(be_o.z), "=f"(be_o.w) : "l"(gp + C));
     }
-    if (CS == 1) __syncthreads(); else adf_cluster_sync();   // partials of every CTA of the cluster are published
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < CS; ++r) {
-      const float4 q = CS == 1 ? *reinterpret_cast<const float4*>(&part[which][4 * lane]) : adw_ld_peer4(&part[which][4 * lane], (uint32_t)r);
-      t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
-    }
-    return t;
   };
-  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int len_n = T;
+  float4 g_n = make_float4(0.f, 0.f, 0.f, 0.f), be_n = g_n;
+  if ((int)blockIdx.x < units) load_scalars(blockIdx.x, len_n, g_n, be_n);
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int b = u / nslab, cb = (u - b * nslab) * 32, c = cb + 4 * c4;
+    const bool cok = c < C;
+    int len = len_n;
+    const float4 g = g_n, be = be_n;
+    if (u + (int)gridDim.x < units) load_scalars(u + gridDim.x, len_n, g_n, be_n);
+    mbar_wait(smem_u32(&bars[stage]), phase);
+    len = min(len, T);
+    const float* slab = ring + (size_t)stage * (slab_bytes / 4) + 4 * c4;
+    const float4 pv = *reinterpret_cast<const float4*>(slab);
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
 #pragma unroll 4
-  for (int t = w; t < nv; t += 8) {
-    const float4 v = *reinterpret_cast<const float4*>(slab + t * ADW_CW + 4 * lane);
-    s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
-  }
-  const float inv_len = len > 0 ? 1.f / len : 0.f;
-  float4 mean = cluster_total(s4, 0);
-  mean.x *= inv_len; mean.y *= inv_len; mean.z *= inv_len; mean.w *= inv_len;
-  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int t = w; t < nv; t += 8) {
-    const float4 v = *reinterpret_cast<const float4*>(slab + t * ADW_CW + 4 * lane);
-    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
-    q4.x += dx * dx; q4.y += dy * dy; q4.z += dz * dz; q4.w += dw * dw;
-  }
-  const float4 var = cluster_total(q4, 1);
-  // peers may still be reading this CTA's partials: arrive now, wait right before exit
-  if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  if (cok) {
-    const float4 rstd = make_float4(rsqrtf(var.x * inv_len + eps), rsqrtf(var.y * inv_len + eps),
-                                    rsqrtf(var.z * inv_len + eps), rsqrtf(var.w * inv_len + eps));
-    if (stats_out != nullptr && rank == 0 && w == 0) {
-      float* so = stats_out + ((long long)b * C + c) * 2;
-      so[0] = mean.x; so[1] = rstd.x; so[2] = mean.y; so[3] = rstd.y; so[4] = mean.z; so[5] = rstd.z; so[6] = mean.w; so[7] = rstd.w;
+    for (int t = row0; t < len; t += ADR_ROWS) {
+      const float4 v = *reinterpret_cast<const float4*>(slab + t * 32);
+      const float dx = v.x - pv.x, dy = v.y - pv.y, dz = v.z - pv.z, dw = v.w - pv.w;
+      s4.x += dx; s4.y += dy; s4.z += dz; s4.w += dw;
+      q4.x = fmaf(dx, dx, q4.x); q4.y = fmaf(dy, dy, q4.y); q4.z = fmaf(dz, dz, q4.z); q4.w = fmaf(dw, dw, q4.w);
     }
-    const float4 g = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + c);
-    const float4 be = *reinterpret_cast<const float4*>(gb + (long long)b * gb_ld + C + c);
-    const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
-    auto act_at = [&](int t) -> float4 {     // t: absolute frame; rows t_lo .. t_lo + TR (+1 halo row when UP) are resident
-      if (t >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 v = *reinterpret_cast<const float4*>(slab + (t - t_lo) * ADW_CW + 4 * lane);
-      v.x = (v.x - mean.x) * sc.x + be.x; v.y = (v.y - mean.y) * sc.y + be.y;
-      v.z = (v.z - mean.z) * sc.z + be.z; v.w = (v.w - mean.w) * sc.w + be.w;
-      v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
-      v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
-      return v;
-    };
-    const int t_end = min(T, t_lo + TR);
-    if (!UP) {
-#pragma unroll 4
-      for (int t = t_lo + w; t < t_end; t += 8) st4any(out, ((long long)b * T + t) * out_ld + c, act_at(t), odt);
-    } else {
-      float w0[4], w1[4], w2[4], ub[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
-      for (int t = t_lo + w; t < t_end; t += 8) {
-        float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
-        if (t < len) {
-          const float4 a0 = act_at(t), a1 = act_at(t + 1);
-          ev = make_float4(a0.x * w1[0] + ub[0], a0.y * w1[1] + ub[1], a0.z * w1[2] + ub[2], a0.w * w1[3] + ub[3]);
-          od = make_float4(a0.x * w2[0] + a1.x * w0[0] + ub[0], a0.y * w2[1] + a1.y * w0[1] + ub[1],
-                           a0.z * w2[2] + a1.z * w0[2] + ub[2], a0.w * w2[3] + a1.w * w0[3] + ub[3]);
+    for (int o = 8; o <= 16; o <<= 1) {
+      s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
+      s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
+      q4.x += __shfl_xor_sync(0xffffffffu, q4.x, o); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, o);
+      q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
+    }
+    if (r4 == 0) {
+      *reinterpret_cast<float4*>(&red[0][w][4 * c4]) = s4;
+      *reinterpret_cast<float4*>(&red[1][w][4 * c4]) = q4;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {                                 // 2 x 32 columns: one thread folds the 16 warps' partials
+      const int which = threadIdx.x >> 5, col = threadIdx.x & 31;
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < ADR_WARPS; ++i) a += red[which][i][col];
+      tot[which][col] = a;
+    }
+    __syncthreads();
+    if (cok) {
+      const float inv_len = len > 0 ? 1.f / len : 0.f;
+      const float4 sd = *reinterpret_cast<const float4*>(&tot[0][4 * c4]);
+      const float4 sq = *reinterpret_cast<const float4*>(&tot[1][4 * c4]);
+      const float4 md = make_float4(sd.x * inv_len, sd.y * inv_len, sd.z * inv_len, sd.w * inv_len);   // mean - pivot
+      const float4 mean = make_float4(pv.x + md.x, pv.y + md.y, pv.z + md.z, pv.w + md.w);
+      const float4 rstd = make_float4(rsqrtf(fmaxf(sq.x * inv_len - md.x * md.x, 0.f) + eps), rsqrtf(fmaxf(sq.y * inv_len - md.y * md.y, 0.f) + eps),
+                                      rsqrtf(fmaxf(sq.z * inv_len - md.z * md.z, 0.f) + eps), rsqrtf(fmaxf(sq.w * inv_len - md.w * md.w, 0.f) + eps));
+      if (stats_out != nullptr && threadIdx.x < 8) {
+        float* so = stats_out + ((long long)b * C + c) * 2;
+        so[0] = mean.x; so[1] = rstd.x; so[2] = mean.y; so[3] = rstd.y; so[4] = mean.z; so[5] = rstd.z; so[6] = mean.w; so[7] = rstd.w;
+      }
+      // y = (x - mean) * rstd * (1 + g) + be = x * sc + sh: one fused multiply-add per element (its single rounding
+      // is relative to |x * sc| <= ~|mean| / std, i.e. ~1e-5 of the normalised scale for the worst decoder channels)
+      const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
+      const float4 sh = make_float4(be.x - mean.x * sc.x, be.y - mean.y * sc.y, be.z - mean.z * sc.z, be.w - mean.w * sc.w);
+      auto act_row = [&](int t) -> float4 {                 // t < len
+        float4 v = *reinterpret_cast<const float4*>(slab + t * 32);
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        if (mx) {
+          v.x = fmaxf(v.x, v.x * slope); v.y = fmaxf(v.y, v.y * slope); v.z = fmaxf(v.z, v.z * slope); v.w = fmaxf(v.w, v.w * slope);
+        } else {
+          v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+          v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
         }
-        st4any(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
-        st4any(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+        return v;
+      };
+      if (!UP) {
+        if (odt != AS_F32) {
+          // 16-bit output: 8 bytes per thread, 64 contiguous bytes per row; frames past the length are zeros
+          uint2* o2 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + ((long long)b * T + row0) * out_ld + c);
+          const long long ostep = (long long)ADR_ROWS * out_ld / 4;     // in uint2 units (out_ld % 4 == 0)
+          int t = row0;
+          if (odt == AS_F16) {
+#pragma unroll 4
+            for (; t < len; t += ADR_ROWS, o2 += ostep) { const float4 v = act_row(t); *o2 = make_uint2(pack16(v.x, v.y, AS_F16), pack16(v.z, v.w, AS_F16)); }
+          } else {
+#pragma unroll 4
+            for (; t < len; t += ADR_ROWS, o2 += ostep) { const float4 v = act_row(t); *o2 = make_uint2(pack16(v.x, v.y, AS_BF16), pack16(v.z, v.w, AS_BF16)); }
+          }
+          for (; t < T; t += ADR_ROWS, o2 += ostep) *o2 = make_uint2(0u, 0u);
+        } else {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+          for (int t = row0; t < T; t += ADR_ROWS) st4any(out, ((long long)b * T + t) * out_ld + c, t < len ? act_row(t) : z4, odt);
+        }
+      } else {
+        float w0[4], w1[4], w2[4], ub[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
+        for (int t = row0; t < T; t += ADR_ROWS) {
+          float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
+          if (t < len) {
+            const float4 a0 = act_row(t), a1 = t + 1 < len ? act_row(t + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ev = make_float4(a0.x * w1[0] + ub[0], a0.y * w1[1] + ub[1], a0.z * w1[2] + ub[2], a0.w * w1[3] + ub[3]);
+            od = make_float4(a0.x * w2[0] + a1.x * w0[0] + ub[0], a0.y * w2[1] + a1.y * w0[1] + ub[1],
+                             a0.z * w2[2] + a1.z * w0[2] + ub[2], a0.w * w2[3] + a1.w * w0[3] + ub[3]);
+          }
+          st4any(out, ((long long)b * 2 * T + 2 * t) * out_ld + c, ev, odt);
+          st4any(out, ((long long)b * 2 * T + 2 * t + 1) * out_ld + c, od, odt);
+        }
       }
     }
+    __syncthreads();   // every thread is done with this stage (and with red / tot): refill it
+    if (threadIdx.x == 0) {
+      const int un = u + S * gridDim.x;
+      if (un < units) issue(un, stage);
+    }
+    if (++stage == S) { stage = 0; phase ^= 1u; }
   }
-  if (CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1319,43 +1366,35 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
                               return (reinterpret_cast<uintptr_t>(out) % (4 * es)) == 0 && ((out_ld * es) % (4 * es)) == 0; }() &&
       (reinterpret_cast<uintptr_t>(gb) & 15) == 0 && (gb_ld % 4) == 0 && check_arch() == AS_OK) {
     EncodeTiledFn enc = get_encode_fn();
-    static const bool no_wide = getenv("ASB_ADAIN_NO_WIDE") != nullptr;
-    if (enc && !no_wide && C >= ADW_CW) {
-      // smallest cluster whose per-CTA row range (+1 halo row for the transposed depthwise "pool") fits two CTAs per SM
-      int CS = 1;
-      auto rows_need = [&](int cs) { return (T + cs - 1) / cs + (up_w ? 1 : 0); };
-      while (CS < 8 && (size_t)rows_need(CS) * ADW_CW * 4 > (size_t)ADW_SLAB_BYTES) CS <<= 1;
-      if ((size_t)rows_need(CS) * ADW_CW * 4 <= (size_t)ADW_SLAB_BYTES) {
-        const int TR = (T + CS - 1) / CS, need = rows_need(CS);
-        const int nbox = (need + 255) / 256, BR = (need + nbox - 1) / nbox;
-        CUtensorMap tmx;
-        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t strides[2] = {(cuuint64_t)x_ld * 4, (cuuint64_t)x_ld * 4 * T};
-        cuuint32_t box[3] = {(cuuint32_t)ADW_CW, (cuuint32_t)BR, 1};
-        cuuint32_t es3[3] = {1, 1, 1};
-        if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-          const size_t smem = (size_t)nbox * BR * ADW_CW * 4 + 128;
-          dim3 grid(cdiv(C, ADW_CW) * CS, (unsigned)B);
-#define ADW_LAUNCH(UP_, CS_)                                                                                                   \
-  do {                                                                                                                         \
-    static bool attr = false;                                                                                                  \
-    if (!attr) {                                                                                                               \
-      ASB_CUDA(cudaFuncSetAttribute(adain_wide_kernel<UP_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADW_SLAB_BYTES + 1024)); \
-      attr = true;                                                                                                             \
-    }                                                                                                                          \
-    ASB_CUDA(launch_k(adain_wide_kernel<UP_, CS_>, grid, 256, smem, ST(stream), tmx, T, TR, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, \
-                      up_b, out, out_dtype, out_ld, stats));                                                                   \
-  } while (0)
-          if (up_w) {
-            if (CS == 1) ADW_LAUNCH(true, 1); else if (CS == 2) ADW_LAUNCH(true, 2); else if (CS == 4) ADW_LAUNCH(true, 4); else ADW_LAUNCH(true, 8);
-          } else {
-            if (CS == 1) ADW_LAUNCH(false, 1); else if (CS == 2) ADW_LAUNCH(false, 2); else if (CS == 4) ADW_LAUNCH(false, 4); else ADW_LAUNCH(false, 8);
-          }
-#undef ADW_LAUNCH
-          ASB_CUDA(cudaGetLastError());
-          return AS_OK;
+    static const bool no_ring = getenv("ASB_ADAIN_NO_RING") != nullptr;
+    if (enc && !no_ring) {
+      // ring of S slabs [nbox * BR][32] fp32 in one persistent CTA per SM (see adain_ring_kernel)
+      const int nbox = (T + 255) / 256;
+      const int BR = ((T + nbox - 1) / nbox + 7) / 8 * 8;
+      const size_t slab_bytes = (size_t)nbox * BR * 128;
+      const int S = (int)std::min<size_t>(ADR_MAX_STAGES, (size_t)(216 * 1024) / slab_bytes);
+      CUtensorMap tmx;
+      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)x_ld * 4, (cuuint64_t)x_ld * 4 * T};
+      cuuint32_t box[3] = {32, (cuuint32_t)BR, 1};
+      cuuint32_t es3[3] = {1, 1, 1};
+      if (S >= 2 && enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        static bool rattr = false;
+        if (!rattr) {
+          ASB_CUDA(cudaFuncSetAttribute(adain_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
+          ASB_CUDA(cudaFuncSetAttribute(adain_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
+          rattr = true;
         }
+        const int nslab = cdiv(C, 32), units = nslab * B;
+        const size_t rsmem = (size_t)S * slab_bytes + 128;
+        dim3 rgrid((unsigned)std::min(units, num_sms()));
+        if (up_w) ASB_CUDA(launch_k(adain_ring_kernel<true>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld,
+                                    eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));
+        else ASB_CUDA(launch_k(adain_ring_kernel<false>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld,
+                               eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));
+        ASB_CUDA(cudaGetLastError());
+        return AS_OK;
       }
     }
     if (enc) {

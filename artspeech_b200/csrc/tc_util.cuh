@@ -163,6 +163,10 @@ inline int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    // ASB_RESERVE_SMS=R: persistent kernels size their grids for n - R SMs, leaving R SMs to whatever runs on the
+    // other streams (the second batch in flight) -- a scheduling experiment, off by default
+    const char* r = getenv("ASB_RESERVE_SMS");
+    if (r != nullptr) n = std::max(2, n - atoi(r)) & ~1;
   }
   return n;
 }

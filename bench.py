@@ -338,7 +338,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         ad_us = e0.elapsed_time(e1) / (5 * nset) * 1e3
         ad_bytes = B_PER_GPU * FRAMES * Cd * (4 + 2)
-        hbm_info = {"bound": "hbm", "kernel": "adain_wide_kernel (InstanceNorm + AdaIN + LeakyReLU, 16x800x1024 fp32 -> f16)",
+        hbm_info = {"bound": "hbm", "kernel": "adain_ring_kernel (InstanceNorm + AdaIN + LeakyReLU, 16x800x1024 fp32 -> f16)",
                     "achieved": ad_bytes / ad_us / 1e3, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
                     "frac": ad_bytes / ad_us / 1e3 / peaks()["hbm_gbs"], "us_per_launch": ad_us,
                     "bytes_per_launch": ad_bytes, "l2": "6 rotating input sets (474 MB), graph replay"}

@@ -230,9 +230,9 @@ def test_instnorm_adain(up):
 @pytest.mark.parametrize("shape", [(3, 100, 96), (2, 801, 512), (1, 1600, 64), (24, 200, 1024), (10, 800, 1216), (2, 1700, 256),
                                    (4, 300, 384)])
 def test_adain_norm_fused(shape, up):
-    """as_adain_norm_apply (single pass, slab in shared memory; C < 128 takes the 32-channel TMA / cluster
-    kernels; C >= 128 the wide-row cluster kernel with 1, 2, 4 or 8 CTAs per cluster depending on T, including a
-    partial last 128-channel group (C = 1216) and the halo row of the upsampling variant)."""
+    """as_adain_norm_apply (single pass, slab in shared memory; fp32 inputs of up to ~860 frames take the
+    persistent cp.async ring kernel with 2, 3 or 4 stages -- the large shapes make it wrap the ring -- longer ones the
+    single-slab TMA kernel, then the cluster / two-pass paths)."""
     B, T, C = shape
     torch.manual_seed(3)
     x = torch.randn(B, T, C) * 0.7 + torch.randn(C) * 30.0       # bias-dominated channels (|mean| >> std)

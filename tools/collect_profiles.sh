@@ -23,4 +23,11 @@ ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 8 
     python tools/prof_conv.py 256 11 128000 res > /dev/null 2>&1
 python tools/ncu_summary.py gpurun_out/${TAG}_conv_c256k11.ncu-rep 16 > gpurun_out/${TAG}_conv_c256k11_summary.txt 2>&1
 rm -f gpurun_out/${TAG}_conv_c256k11.ncu-rep
+# 4. the fused InstanceNorm + AdaIN kernel (HBM roofline entry of bench.py): full capture of one launch + per-launch DRAM bytes
+ncu --set full --clock-control none --import-source on -k regex:adain_ring -s 8 -c 1 -o gpurun_out/${TAG}_adain \
+    python tools/prof_adain.py > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/${TAG}_adain.ncu-rep 16 > gpurun_out/${TAG}_adain_summary.txt 2>&1
+rm -f gpurun_out/${TAG}_adain.ncu-rep
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:adain_ring -c 40 --csv \
+    --log-file gpurun_out/${TAG}_adain.csv python tools/prof_adain.py > /dev/null 2>&1
 ls -la gpurun_out | tail -14

@@ -163,6 +163,59 @@ def shard_utterances(costs: Sequence[float], world_size: int) -> List[List[int]]
     return shards
 
 
+def bucket_utterances(frames: Sequence[int], max_batch: int = 16, max_padded_frames: Optional[int] = None) -> List[List[int]]:
+    """Length-bucketed micro-batches for a mixed-length shard: utterances sorted by frame count,
+    longest first, cut into runs of at most ``max_batch`` whose PADDED size ``len(run) * max(frames in run)`` stays
+    within ``max_padded_frames`` -- neighbours in the sorted order have similar lengths, so padding stays small and
+    every micro-batch costs about the same.  Every index appears exactly once; a single utterance longer than the
+    budget gets a micro-batch of its own."""
+    order = sorted(range(len(frames)), key=lambda i: (-int(frames[i]), i))
+    batches: List[List[int]] = []
+    cur: List[int] = []
+    cur_max = 0
+    for i in order:
+        f = max(int(frames[i]), 1)
+        longest = max(cur_max, f)
+        over = max_padded_frames is not None and cur and (len(cur) + 1) * longest > max_padded_frames
+        if cur and (len(cur) >= max_batch or over):
+            batches.append(cur)
+            cur, longest = [], f
+        cur.append(i)
+        cur_max = longest
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+@torch.no_grad()
+def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels: Sequence[torch.Tensor],
+                    durations: Sequence[torch.Tensor], max_batch: int = 16, max_padded_frames: Optional[int] = 25600):
+    """Mixed-length utterances through ``syn`` in length-bucketed ragged micro-batches (BASELINE config 5).
+
+    ``tokens[i]`` int64 [Tt_i], ``ref_mels[i]`` fp32 [80, Tr_i], ``durations[i]`` int64 [Tt_i] (host tensors).
+    Returns ``(wavs, frames)``: ``wavs[i]`` is a device tensor with the ``300 * frames[i]`` samples of utterance
+    ``i`` (fp32, or int16 when ``syn.pcm16``), independent of what it was batched with (batch-1 semantics)."""
+    n = len(tokens)
+    frames = [2 * int(d.sum()) for d in durations]
+    wavs: List[Optional[torch.Tensor]] = [None] * n
+    for idx in bucket_utterances(frames, max_batch, max_padded_frames):
+        Tt = max(int(tokens[i].shape[0]) for i in idx)
+        Tr = max(int(ref_mels[i].shape[1]) for i in idx)
+        tok = torch.zeros(len(idx), Tt, dtype=torch.long)
+        dur = torch.zeros(len(idx), Tt, dtype=torch.long)
+        mel = torch.zeros(len(idx), ref_mels[idx[0]].shape[0], Tr)
+        for j, i in enumerate(idx):
+            tok[j, :tokens[i].shape[0]] = tokens[i]
+            dur[j, :durations[i].shape[0]] = durations[i]
+            mel[j, :, :ref_mels[i].shape[1]] = ref_mels[i]
+        tl = torch.tensor([int(tokens[i].shape[0]) for i in idx])
+        ml = torch.tensor([int(ref_mels[i].shape[1]) for i in idx])
+        wav, _, _ = syn.synthesize(tok.to(syn.device, non_blocking=True), tl, mel.to(syn.device, non_blocking=True), ml, dur)
+        for j, i in enumerate(idx):
+            wavs[i] = wav[j, :HOP * frames[i]].clone()
+    return wavs, frames
+
+
 def gather_waveforms(wav: torch.Tensor, lengths: torch.Tensor, dst: int = 0, group=None, shapes=None):
     """Gather per-rank ``wav`` [B_r, S_r] (+ sample ``lengths`` [B_r]) on ``dst``.
 

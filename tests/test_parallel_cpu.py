@@ -23,6 +23,24 @@ def test_lpt_sharding_balances_and_covers():
     assert engine.shard_utterances([5.0], 2) == [[0], []]
 
 
+def test_length_bucketed_micro_batches():
+    """engine.bucket_utterances on the BASELINE config-5 length distribution: every utterance exactly once, batch and
+    padded-frame budgets respected, little padding."""
+    g = torch.Generator().manual_seed(1)
+    frames = (torch.randint(15, 595, (512,), generator=g) * 5.3).long().tolist()
+    for max_batch, budget in ((16, 25600), (8, 12800), (16, None), (1, None)):
+        batches = engine.bucket_utterances(frames, max_batch, budget)
+        assert sorted(i for b in batches for i in b) == list(range(512))
+        assert all(1 <= len(b) <= max_batch for b in batches)
+        if budget is not None:
+            assert all(len(b) == 1 or len(b) * max(frames[i] for i in b) <= budget for b in batches)
+        padded = sum(len(b) * max(frames[i] for i in b) for b in batches)
+        assert padded <= 1.06 * sum(frames)                  # sorted neighbours: < 6 % padding
+    assert engine.bucket_utterances([], 16) == []
+    assert engine.bucket_utterances([40000], 16, 25600) == [[0]]          # over-budget utterance: its own batch
+    assert engine.bucket_utterances([10, 30, 20], 2) == [[1, 2], [0]]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

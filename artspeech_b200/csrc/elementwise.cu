@@ -578,12 +578,17 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
     if (u + (int)gridDim.x < units) load_scalars(u + gridDim.x, len_n, g_n, be_n);
     mbar_wait(smem_u32(&bars[stage]), phase);
     len = min(len, T);
-    const float* slab = ring + (size_t)stage * (slab_bytes / 4) + 4 * c4;
-    const float4 pv = *reinterpret_cast<const float4*>(slab);
+    // explicit ld.shared: through the re-aligned generic pointer the compiler emits generic LD instead of LDS
+    const uint32_t slab = smem_u32(ring) + (uint32_t)stage * slab_bytes + 16u * c4;
+    auto row4 = [&](int t) -> float4 {
+      const uint4 r = lds128(slab + (uint32_t)t * 128u);
+      return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+    };
+    const float4 pv = row4(0);
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
 #pragma unroll 4
     for (int t = row0; t < len; t += ADR_ROWS) {
-      const float4 v = *reinterpret_cast<const float4*>(slab + t * 32);
+      const float4 v = row4(t);
       const float dx = v.x - pv.x, dy = v.y - pv.y, dz = v.z - pv.z, dw = v.w - pv.w;
       s4.x += dx; s4.y += dy; s4.z += dz; s4.w += dw;
       q4.x = fmaf(dx, dx, q4.x); q4.y = fmaf(dy, dy, q4.y); q4.z = fmaf(dz, dz, q4.z); q4.w = fmaf(dw, dw, q4.w);
@@ -625,7 +630,7 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
       const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
       const float4 sh = make_float4(be.x - mean.x * sc.x, be.y - mean.y * sc.y, be.z - mean.z * sc.z, be.w - mean.w * sc.w);
       auto act_row = [&](int t) -> float4 {                 // t < len
-        float4 v = *reinterpret_cast<const float4*>(slab + t * 32);
+        float4 v = row4(t);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         if (mx) {
           v.x = fmaxf(v.x, v.x * slope); v.y = fmaxf(v.y, v.y * slope); v.z = fmaxf(v.z, v.z * slope); v.w = fmaxf(v.w, v.w * slope);

@@ -158,7 +158,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
                              "sample": f"{n_per_step} utterances x 10 s per step, batch-1 acoustic + vocoder, fp32 torch"},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -405,10 +405,21 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": a / t, "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"{args.cpu_utts} utterances of the same workload (10 s each), batch-1 "
                                           f"acoustic + vocoder, fp32 torch restatement of the reference"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -423,6 +434,12 @@ def main():
                     help="batches in flight per GPU (2: the acoustic model of step i+1 overlaps the vocoder of step i)")
     ap.add_argument("--cpu-utts", type=int, default=4)
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 (NCCL prints its version banner there
+    # when NCCL_DEBUG is set) are sent to stderr for the whole run, the JSON line goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

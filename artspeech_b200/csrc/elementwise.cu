@@ -428,10 +428,16 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
   __syncthreads();
   mbar_wait(bar, 0);
   const int row0 = w * 4 + r4;
+  // explicit ld.shared: through the re-aligned generic pointer the compiler emits generic LD instead of LDS
+  const uint32_t slab_u = smem_u32(slab) + 16u * c4;
+  auto row4 = [&](int t) -> float4 {
+    const uint4 r = lds128(slab_u + (uint32_t)t * 128u);
+    return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+  };
   float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int t = row0; t < len; t += 32) {
-    const float4 v = *reinterpret_cast<const float4*>(slab + t * 32 + 4 * c4);
+    const float4 v = row4(t);
     s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
   }
   auto reduce4 = [&](float4 p) -> float4 {
@@ -457,7 +463,7 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
   float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int t = row0; t < len; t += 32) {
-    const float4 v = *reinterpret_cast<const float4*>(slab + t * 32 + 4 * c4);
+    const float4 v = row4(t);
     const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
     q4.x += dx * dx; q4.y += dy * dy; q4.z += dz * dz; q4.w += dw * dw;
   }
@@ -474,7 +480,7 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
   const float4 sc = make_float4(rstd.x * (1.f + g.x), rstd.y * (1.f + g.y), rstd.z * (1.f + g.z), rstd.w * (1.f + g.w));
   auto act_at = [&](int t) -> float4 {
     if (t >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 v = *reinterpret_cast<const float4*>(slab + t * 32 + 4 * c4);
+    float4 v = row4(t);
     v.x = (v.x - mean.x) * sc.x + be.x; v.y = (v.y - mean.y) * sc.y + be.y;
     v.z = (v.z - mean.z) * sc.z + be.z; v.w = (v.w - mean.w) * sc.w + be.w;
     v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
@@ -517,7 +523,8 @@ constexpr int ADR_WARPS = ADR_THREADS / 32;
 constexpr int ADR_ROWS = ADR_WARPS * 4;   // rows covered per pass iteration
 constexpr int ADR_MAX_STAGES = 4;
 
-template <bool UP>
+// MX: 0 <= slope <= 1, LeakyReLU(y) = max(y, slope * y) -- a template parameter so that the unrolled loops are branch-free
+template <bool UP, bool MX>
 __global__ void __launch_bounds__(ADR_THREADS, 1)
 adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbox, int C, int nslab, int units, int S,
                   const float* __restrict__ gb, long long gb_ld, float eps, float slope,
@@ -553,7 +560,6 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
   __syncthreads();
   int stage = 0;
   uint32_t phase = 0;
-  const bool mx = slope >= 0.f && slope <= 1.f;            // LeakyReLU(y) = max(y, slope * y)
   // per-unit scalars (length, gamma, beta) are fetched one unit ahead with volatile loads: issued at the top of unit
   // k for unit k + 1, consumed a whole unit later, so their L2 / DRAM latency never stalls the in-order pipeline
   // (ncu: with the loads next to their use, 30 % of the samples sat on the first instruction that reads gamma)
@@ -632,7 +638,7 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
       auto act_row = [&](int t) -> float4 {                 // t < len
         float4 v = row4(t);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-        if (mx) {
+        if (MX) {
           v.x = fmaxf(v.x, v.x * slope); v.y = fmaxf(v.y, v.y * slope); v.z = fmaxf(v.z, v.z * slope); v.w = fmaxf(v.w, v.w * slope);
         } else {
           v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
@@ -1385,19 +1391,23 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
       cuuint32_t es3[3] = {1, 1, 1};
       if (S >= 2 && enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-        static bool rattr = false;
-        if (!rattr) {
-          ASB_CUDA(cudaFuncSetAttribute(adain_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
-          ASB_CUDA(cudaFuncSetAttribute(adain_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));
-          rattr = true;
-        }
         const int nslab = cdiv(C, 32), units = nslab * B;
         const size_t rsmem = (size_t)S * slab_bytes + 128;
         dim3 rgrid((unsigned)std::min(units, num_sms()));
-        if (up_w) ASB_CUDA(launch_k(adain_ring_kernel<true>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld,
-                                    eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));
-        else ASB_CUDA(launch_k(adain_ring_kernel<false>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld,
-                               eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));
+        const bool mx = slope >= 0.f && slope <= 1.f;
+#define ADR_LAUNCH(UP_, MX_)                                                                                                    \
+  do {                                                                                                                          \
+    static bool attr = false;                                                                                                   \
+    if (!attr) {                                                                                                                \
+      ASB_CUDA(cudaFuncSetAttribute(adain_ring_kernel<UP_, MX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));     \
+      attr = true;                                                                                                              \
+    }                                                                                                                           \
+    ASB_CUDA(launch_k(adain_ring_kernel<UP_, MX_>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld, \
+                      eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));                                            \
+  } while (0)
+        if (up_w) { if (mx) ADR_LAUNCH(true, true); else ADR_LAUNCH(true, false); }
+        else { if (mx) ADR_LAUNCH(false, true); else ADR_LAUNCH(false, false); }
+#undef ADR_LAUNCH
         ASB_CUDA(cudaGetLastError());
         return AS_OK;
       }

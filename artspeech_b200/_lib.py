@@ -63,6 +63,7 @@ _lib = None
 SIGNATURES = {
     "as_version": (C.c_int, []),
     "as_last_error": (C.c_char_p, []),
+    "as_set_sm_limit": (C.c_int, [C.c_int32]),
     "as_mas_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "as_mas_maximum_path": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,

@@ -44,5 +44,12 @@ int check_arch() {
 
 }  // namespace asb
 
+namespace asb { int g_sm_limit = 0; }
+
 extern "C" int as_version(void) { return 100; }
+extern "C" int as_set_sm_limit(int32_t n) {
+  const int prev = asb::g_sm_limit;
+  asb::g_sm_limit = n > 0 ? n : 0;
+  return prev;
+}
 extern "C" const char* as_last_error(void) { return asb::g_err; }

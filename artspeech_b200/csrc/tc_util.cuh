@@ -156,19 +156,24 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-inline int num_sms() {
+extern int g_sm_limit;   // api.cu: as_set_sm_limit()
+
+inline int num_sms_device() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
-    // ASB_RESERVE_SMS=R: persistent kernels size their grids for n - R SMs, leaving R SMs to whatever runs on the
-    // other streams (the second batch in flight) -- a scheduling experiment, off by default
-    const char* r = getenv("ASB_RESERVE_SMS");
-    if (r != nullptr) n = std::max(2, n - atoi(r)) & ~1;
   }
   return n;
+}
+
+// SMs a persistent kernel sizes its grid for: all of them, or the share as_set_sm_limit() gave the phase that is
+// being launched (two batches in flight: the vocoder of one and the acoustic model of the other run side by side)
+inline int num_sms() {
+  const int n = num_sms_device();
+  return g_sm_limit > 0 ? std::max(2, std::min(n, g_sm_limit) & ~1) : n;
 }
 
 }  // namespace asb

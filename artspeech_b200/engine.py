@@ -15,7 +15,9 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import ops
+import os
+
+from . import _lib, ops
 
 SAMPLE_RATE = 24000
 HOP = 300
@@ -31,9 +33,14 @@ class Synthesizer:
     test.py:119) written directly by the vocoder's last kernel: half the device->host bytes per utterance."""
 
     def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True, pipeline_depth: int = 1,
-                 pcm16: bool = False):
+                 pcm16: bool = False, acoustic_sms: Optional[int] = None):
         self.device = torch.device(device)
         self.pcm16 = bool(pcm16)
+        # SM split between the two phases when batches overlap: the acoustic model's persistent kernels are sized
+        # for ``acoustic_sms`` SMs and the vocoder's for the rest, so that the latency-bound acoustic chain of batch
+        # i+1 always finds free SMs beside the vocoder of batch i (0 / None: every kernel sizes for the whole GPU)
+        env = os.environ.get("ASB_ACOUSTIC_SMS")
+        self.acoustic_sms = int(env) if env is not None else (acoustic_sms or 0)
         self.pipeline_depth = max(1, int(pipeline_depth))
         self._slot_streams = None
         self._slot_done = {}
@@ -57,9 +64,20 @@ class Synthesizer:
                                               host_lengths=ml))
 
     def _forward(self, tokens, tok_lens, mels, mel_lens, durations, host_meta=None, voice=None):
-        mel, aux = self.model([tokens, tok_lens, mels, mel_lens], step="test", durations=durations, return_aux=True,
-                              host_meta=host_meta, voice=voice)
-        wav = self.generator(mel, aux["mel_lengths"], pcm16=self.pcm16)
+        split = self.acoustic_sms if self.pipeline_depth > 1 else 0
+        lib = _lib.load()
+        total = torch.cuda.get_device_properties(self.device).multi_processor_count
+        try:
+            if split:
+                lib.as_set_sm_limit(split)
+            mel, aux = self.model([tokens, tok_lens, mels, mel_lens], step="test", durations=durations, return_aux=True,
+                                  host_meta=host_meta, voice=voice)
+            if split:
+                lib.as_set_sm_limit(max(2, total - split))
+            wav = self.generator(mel, aux["mel_lengths"], pcm16=self.pcm16)
+        finally:
+            if split:
+                lib.as_set_sm_limit(0)
         return wav.view(wav.shape[0], -1), aux["mel_lengths"], mel
 
     @torch.no_grad()

@@ -49,6 +49,10 @@ typedef enum as_act {
 } as_act;
 
 int as_version(void);
+/* Persistent kernels launched after this call size their grids for at most n SMs (0: all SMs); returns the previous
+ * limit.  The synthesis engine uses it to run the vocoder of one batch and the acoustic model of the next side by
+ * side on disjoint SM shares instead of time-slicing the whole GPU (process-wide, host-side setting). */
+int as_set_sm_limit(int32_t n);
 const char* as_last_error(void);
 
 /* ------------------------------------------------------------------------------------------

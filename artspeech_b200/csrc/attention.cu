@@ -20,8 +20,9 @@ constexpr int RA_QT = RA_WARPS * RA_QW;  // queries per CTA
 constexpr int RA_KT = 32;                // keys per tile
 constexpr int RA_MAXW = 9;               // 2*window+1 <= 9
 
+// 3 CTAs per SM (<= 85 registers): the bench shape launches 320 CTAs; at 2 per SM the last 24 made a second wave
 template <int D>
-__global__ void __launch_bounds__(RA_WARPS * 32)
+__global__ void __launch_bounds__(RA_WARPS * 32, 3)
 relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float* __restrict__ relk,
                         const float* __restrict__ relv, int window, int T, int H,
                         const int* __restrict__ lens, void* out, int odt, long long out_ld) {
@@ -31,7 +32,9 @@ relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float
   float* kv = sm;                           // [RA_KT][KP]
   float* qs = kv + RA_KT * KP;              // [RA_QT][D]
   float* qe = qs + RA_QT * D;               // [RA_QT][RA_MAXW] q . E_k[r]
-  float* sc = qe + RA_QT * RA_MAXW;         // [RA_QT][Tpad] scores / probabilities
+  float* rks = qe + RA_QT * RA_MAXW;        // [RA_MAXW][D] relative-key embeddings  (staged: read from global they
+  float* rvs = rks + RA_MAXW * D;           // [RA_MAXW][D] relative-value embeddings  cost ~290 dependent loads per warp)
+  float* sc = rvs + RA_MAXW * D;            // [RA_QT][Tpad] scores / probabilities
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * RA_QT;
   const int len = lens ? min(lens[b], T) : T;
@@ -51,7 +54,12 @@ relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float
     return;
   }
 
-  // stage the CTA's queries
+  // stage the relative embeddings and the CTA's queries
+  for (int i = tid; i < RA_MAXW * D; i += blockDim.x) {
+    const bool in = i < nrel * D;
+    rks[i] = in ? relk[i] : 0.f;
+    rvs[i] = in ? relv[i] : 0.f;
+  }
   for (int i = tid; i < RA_QT * D; i += blockDim.x) {
     int qi = q0 + i / D, d = i % D;
     qs[i] = qi < T ? base[(long long)qi * ld + h * D + d] : 0.f;
@@ -62,7 +70,7 @@ relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float
     int ql = i / RA_MAXW, r = i % RA_MAXW;
     float s = 0.f;
     if (r < nrel)
-      for (int d = lane; d < D; d += 32) s += qs[ql * D + d] * relk[r * D + d];
+      for (int d = lane; d < D; d += 32) s += qs[ql * D + d] * rks[r * D + d];
     s = warp_sum(s);
     if (lane == 0) qe[i] = s;
   }
@@ -172,7 +180,7 @@ relpos_attention_kernel(const float* __restrict__ qkv, long long ld, const float
         if (j < 0 || j >= len) continue;
         const float p = sc[ql * Tpad + j];
 #pragma unroll
-        for (int c = 0; c < DPL; ++c) acc[u][c] += p * relv[(r + window) * D + lane + 32 * c];
+        for (int c = 0; c < DPL; ++c) acc[u][c] += p * rvs[(r + window) * D + lane + 32 * c];
       }
     }
 #pragma unroll
@@ -369,8 +377,8 @@ conformer_attention_tiled_kernel(const float* __restrict__ q, const float* __res
     if (a >= len) continue;   // warp-uniform
     float m = -INFINITY;
     for (int j = lane; j < L; j += 32) {
-      const long long f = (long long)(a + 1) * L + j;
-      const int i2 = (int)(f / (L + 1)), jj = (int)(f % (L + 1));
+      const unsigned f = (unsigned)(a + 1) * (unsigned)L + (unsigned)j;      // < 2^32 for T < 65535: 32-bit divide
+      const int i2 = (int)(f / (unsigned)(L + 1)), jj = (int)(f - (unsigned)i2 * (unsigned)(L + 1));
       float sc = S[r * Tpad + j];
       if (jj != 0) sc += Mx[(i2 - a0) * Tpad + jj - 1];
       sc *= inv_sqrt;
@@ -428,7 +436,7 @@ extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float
   ASB_REQUIRE(D == 128, AS_ERR_SHAPE, "as_relpos_attention: head dim %d unsupported (128 only)", D);
   ASB_REQUIRE(window >= 0 && 2 * window + 1 <= RA_MAXW, AS_ERR_SHAPE, "as_relpos_attention: window");
   const int Tpad = (T + 31) & ~31;
-  const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 4) + RA_QT * D + RA_QT * RA_MAXW + (size_t)RA_QT * Tpad);
+  const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 4) + RA_QT * D + RA_QT * RA_MAXW + 2 * RA_MAXW * D + (size_t)RA_QT * Tpad);
   ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_relpos_attention: T=%d too long for the score buffer", T);
   static bool attr = false;
   if (!attr) {

@@ -94,6 +94,52 @@ __global__ void layernorm_kernel(const void* __restrict__ x, int xdt, long long 
   }
 }
 
+__device__ __forceinline__ void st4any(void* p, long long off, float4 v, int dt);   // defined below
+
+// fp32 rows with C a multiple of 128 (the encoders' 512 / 256 / 1024 channels): each lane owns C / 128 groups of 4
+// consecutive channels -- 16-byte loads, all in flight before the first use, and 8- / 16-byte stores (the scalar
+// kernel above issues 16 four-byte loads and up to 32 stores per lane at C = 512)
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_vec4_kernel(const float* __restrict__ x, long long x_ld, long long rows, int T, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, int act, float slope, const int* __restrict__ lens,
+                      void* oa, int oadt, long long oa_ld, void* ob, int obdt, long long ob_ld) {
+  pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
+  constexpr int C = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = row / T, t = row % T;
+  const bool valid = lens == nullptr || t < lens[b];
+  float4 v[NV];
+  const float4* xr = reinterpret_cast<const float4*>(x + row * x_ld) + lane;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldg(xr + 32 * i);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * lane + 128 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + be.x; y.y = (v[i].y - mean) * rstd * g.y + be.y;
+    y.z = (v[i].z - mean) * rstd * g.z + be.z; y.w = (v[i].w - mean) * rstd * g.w + be.w;
+    if (valid) { y.x = apply_act(y.x, act, slope); y.y = apply_act(y.y, act, slope); y.z = apply_act(y.z, act, slope); y.w = apply_act(y.w, act, slope); }
+    else y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (oa) st4any(oa, row * oa_ld + c, y, oadt);
+    if (ob) st4any(ob, row * ob_ld + c, y, obdt);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // InstanceNorm statistics: block = (b, 32 channels), 32 x 8 threads, two passes (mean, then
 // centred second moment) like the reference's biased variance.
@@ -1312,6 +1358,24 @@ extern "C" int as_layernorm(const void* x, int32_t x_dtype, int64_t x_ld, int32_
   ASB_REQUIRE(x && gamma && beta && (out_a || out_b), AS_ERR_SHAPE, "as_layernorm: null pointer");
   ASB_REQUIRE(C > 0 && C <= 32 * LN_MAX_PER_LANE, AS_ERR_SHAPE, "as_layernorm: C=%d unsupported", C);
   ASB_REQUIRE(dt_ok(x_dtype), AS_ERR_DTYPE, "as_layernorm: dtype");
+  {
+    auto ok4 = [](const void* ptr, long long ld, int dt) {
+      const int es = dt == AS_F32 ? 4 : 2;
+      return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % (4 * es)) == 0 && ((ld * es) % (4 * es)) == 0);
+    };
+    if (x_dtype == AS_F32 && (C == 256 || C == 512 || C == 1024) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_ld % 4) == 0 &&
+        (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0 &&
+        ok4(out_a, out_a_ld, out_a_dtype) && ok4(out_b, out_b_ld, out_b_dtype)) {
+      const float* xf = reinterpret_cast<const float*>(x);
+#define LNV_LAUNCH(NV_)                                                                                                            \
+  ASB_CUDA(launch_k(layernorm_vec4_kernel<NV_>, cdiv(rows, 8), 256, 0, ST(stream), xf, x_ld, rows, T, gamma, beta, eps, act, slope, lens, \
+                    out_a, out_a_dtype, out_a_ld, out_b, out_b_dtype, out_b_ld))
+      if (C == 256) LNV_LAUNCH(2); else if (C == 512) LNV_LAUNCH(4); else LNV_LAUNCH(8);
+#undef LNV_LAUNCH
+      ASB_CUDA(cudaGetLastError());
+      return AS_OK;
+    }
+  }
   ASB_CUDA(launch_k(layernorm_kernel, cdiv(rows, 8), 256, 0, ST(stream), x, x_dtype, x_ld, rows, T, C, gamma, beta, eps, act,
                                                          slope, lens, out_a, out_a_dtype, out_a_ld, out_b,
                                                          out_b_dtype, out_b_ld));

@@ -176,6 +176,13 @@ def test_embed_layernorm():
         oa, ob = ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), 1e-4, act=ops.ACT_RELU, lens=lens.to(DEV),
                                out_a=torch.float32, out_b=torch.float16)
         _close(oa, ra, 1e-5); _close(ob, rb, 1e-3)
+    # channel counts / dtypes outside the 16-byte fast path take the scalar kernel
+    for C, dt in ((192, torch.float32), (512, torch.float16)):
+        x = (torch.randn(3, 57, C) * 3 + 1).to(dt)
+        g, b = torch.randn(C), torch.randn(C)
+        ra, _ = sim.layernorm(x, g, b, 1e-5, lens=lens, out_a=torch.float32)
+        oa, _ = ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), 1e-5, lens=lens.to(DEV), out_a=torch.float32)
+        _close(oa, ra, 1e-4)
 
 
 @pytest.mark.parametrize("T", [37, 150, 333])

@@ -1010,15 +1010,23 @@ dwconv_time_tiled_kernel(const void* __restrict__ x, int xdt, long long x_ld, in
   const int len_in = lens_in ? min(lens_in[b], T) : T;
   const int nrows = DWT_ROWS + kt - 1;
   const bool cok = c < C;
-  for (int r = ty; r < nrows; r += 4) {
-    const int ti = t0 - pt + r;
-    float v = 0.f;
-    if (cok && ti >= 0 && ti < len_in) {
-      const long long xr = ((long long)b * T + ti) * x_ld;
-      v = ldany(x, xr + c, xdt);
-      if (glu) { const float g = ldany(x, xr + C + c, xdt); v = v / (1.f + __expf(-g)); }
+  // four rows per iteration, all loads issued before the first use (one row at a time the ~24 dependent pairs of
+  // loads per thread set the kernel's time)
+  for (int r0 = ty; r0 < nrows; r0 += 16) {
+    float v[4], g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ti = t0 - pt + r0 + 4 * k;
+      const bool ok = cok && r0 + 4 * k < nrows && ti >= 0 && ti < len_in;
+      const long long xr = ((long long)b * T + (ok ? ti : 0)) * x_ld;
+      v[k] = ok ? ldany(x, xr + c, xdt) : 0.f;
+      g[k] = (ok && glu) ? ldany(x, xr + C + c, xdt) : 0.f;
     }
-    tile[r * DWT_CH + tx] = v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + 4 * k;
+      if (r < nrows) tile[r * DWT_CH + tx] = glu ? v[k] / (1.f + __expf(-g[k])) : v[k];
+    }
   }
   float wr[DWT_MAXK];
 #pragma unroll

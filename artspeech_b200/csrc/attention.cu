@@ -5,6 +5,8 @@
 //                         (Utils/EMA/conformer/conformer/attention.py:72-113).
 // Neither materialises the [B,H,T,T] score tensor in HBM (the reference does, plus pad/view skew
 // copies); scores live in shared memory per query block.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace asb {
@@ -335,37 +337,37 @@ conformer_attention_tiled_kernel(const float* __restrict__ q, const float* __res
       *reinterpret_cast<float4*>(KT + r * KS + 4 * c) = t;
     }
   };
-  // rows of `Qm` (nrows of them, this warp's share) dotted with the 32 keys of the tile
-  auto dot_rows = [&](const float* Qm, int r0, int nrows, float* dst, int j0) {
-    float acc[QPW + 1];
+  // NR rows of `Qm` (this warp's share) dotted with the 32 keys of the tile; NR is a compile-time constant so that the
+  // extra row only warp 7 needs costs the other warps nothing
+  auto dot_rows = [&](auto nr_tag, const float* Qm, int r0, float* dst, int j0) {
+    constexpr int NR = decltype(nr_tag)::value;
+    float acc[NR];
 #pragma unroll
-    for (int i = 0; i < QPW + 1; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
     const float* kr = KT + lane * KS;
 #pragma unroll 4
     for (int d = 0; d < D; d += 4) {
       const float4 kk = *reinterpret_cast<const float4*>(kr + d);
 #pragma unroll
-      for (int i = 0; i < QPW + 1; ++i) {
-        if (i < nrows) {
-          const float4 qq = *reinterpret_cast<const float4*>(Qm + (r0 + i) * D + d);
-          acc[i] += qq.x * kk.x + qq.y * kk.y + qq.z * kk.z + qq.w * kk.w;
-        }
+      for (int i = 0; i < NR; ++i) {
+        const float4 qq = *reinterpret_cast<const float4*>(Qm + (r0 + i) * D + d);
+        acc[i] = fmaf(qq.x, kk.x, fmaf(qq.y, kk.y, fmaf(qq.z, kk.z, fmaf(qq.w, kk.w, acc[i]))));
       }
     }
 #pragma unroll
-    for (int i = 0; i < QPW + 1; ++i)
-      if (i < nrows) dst[(r0 + i) * Tpad + j0 + lane] = acc[i];
+    for (int i = 0; i < NR; ++i) dst[(r0 + i) * Tpad + j0 + lane] = acc[i];
   };
   for (int j0 = 0; j0 < L; j0 += 32) {
     __syncthreads();
     load_tile(kb, ld, j0);
     __syncthreads();
-    dot_rows(Qu, warp * QPW, QPW, S, j0);
+    dot_rows(std::integral_constant<int, QPW>{}, Qu, warp * QPW, S, j0);
     __syncthreads();
     load_tile(pos + h * D, HD, j0);
     __syncthreads();
     // warp 7 also takes the extra row QT (query a0+QT, needed by the shift of the tile's last query)
-    dot_rows(Qv, warp * QPW, warp == CT_WARPS - 1 ? QPW + 1 : QPW, Mx, j0);
+    if (warp == CT_WARPS - 1) dot_rows(std::integral_constant<int, QPW + 1>{}, Qv, warp * QPW, Mx, j0);
+    else dot_rows(std::integral_constant<int, QPW>{}, Qv, warp * QPW, Mx, j0);
   }
   __syncthreads();
   const float inv_sqrt = rsqrtf((float)HD);

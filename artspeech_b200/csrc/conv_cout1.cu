@@ -91,7 +91,7 @@ conv_cout1_kernel(const uint16_t* __restrict__ x, long long x_ld, int T, int Cin
 // row (one ldmatrix + one MMA per 16 rows x 16 channels, no unpacking), P goes to shared memory in fp32 and an
 // output is the diagonal sum y[t] = bias + sum_j P[t + j * dil][j]: ~25 instructions per output.
 // ---------------------------------------------------------------------------------------------
-constexpr int C1M_ROWS = 512;                            // output rows per CTA
+constexpr int C1M_ROWS = 256;                            // output rows per CTA
 constexpr int C1M_PP = 9;                                // pitch (floats) of a P row: conflict-free diagonal reads
 
 template <bool BF16>

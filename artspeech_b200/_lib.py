@@ -114,6 +114,7 @@ SIGNATURES.update({
     "as_adain_norm_apply": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _L, _F, _F, _V, _V, _V, _V, _I, _L, _V, _V]),
     "as_repeat_rows": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _I, _L, _V]),
     "as_length_regulate": (C.c_int, [_V, _I, _L, _I, _I, _I, _V, _V, _I, _I, _V, _I, _L, _V, _V]),
+    "as_round_durations": (C.c_int, [_V, _L, _I, _I, _V, _V, _V, _V]),
     "as_conv_small": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _V, _V, _I, c_i32_p, c_i32_p, _I, _V,
                                 _V, _I, _L, _V, _I, _L, _I, _F, _V]),
     "as_dwconv": (C.c_int, [_V, _I, _L, _I, _I, _I, _I, _I, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I,

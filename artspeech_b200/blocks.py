@@ -96,7 +96,7 @@ class StyleFC:
 
 
 def run_adain_block(p, x, gb1, gb2, lens, dt, out=None, out16=None, x16=None, res_dtype=None,
-                    mid_dtype=torch.float32):
+                    mid_dtype=torch.float32, lens_up=None):
     """AdainResBlk1d.forward (models.py:183-202) on channels-last ``x`` [B, T, Cin].
 
     ``x`` is the residual stream (fp32 or 16-bit): it feeds the InstanceNorm statistics, AdaIN and the
@@ -106,7 +106,8 @@ def run_adain_block(p, x, gb1, gb2, lens, dt, out=None, out16=None, x16=None, re
     copy for the next block's 1x1 shortcut.  Returns (out, out16, lens'); T' = 2T for upsample."""
     a1 = ops.adain_norm(x, gb1, LRELU, lens, dt, p["up_w"], p["up_b"])
     up = p["up_w"] is not None
-    lens2 = lens * 2 if (up and lens is not None) else lens
+    # ``lens_up`` = 2 * lens when the caller already holds it (saves a tiny elementwise launch per upsampling block)
+    lens2 = (lens_up if lens_up is not None else lens * 2) if (up and lens is not None) else lens
     c1, _ = ops.conv(a1, p["conv1"], raw=mid_dtype, lens=lens2)
     a2 = ops.adain_norm(c1, gb2, LRELU, lens2, dt)
     if p["sc"] is not None:

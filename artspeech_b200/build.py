@@ -48,9 +48,25 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every ``csrc/*.cu`` and link ``libartspeech_b200.so``.  Returns the library path."""
+    """Compile every ``csrc/*.cu`` and link ``libartspeech_b200.so``.  Returns the library path.
+
+    Safe under ``torchrun``: an exclusive file lock serialises concurrent builders (the ranks that lose the race find
+    an up-to-date library when they get the lock) and the library is linked to a temporary name and renamed into
+    place, so a process that is loading it never sees a half-written file."""
     if not force and is_current():
         return LIB_PATH
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
     procs = []
@@ -86,11 +102,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for path, digest in stamps:
         with open(path, "w") as f:
             f.write(digest)
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static",
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-cudart", "static",
             "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout.decode()}")
+    os.replace(tmp, LIB_PATH)
     with open(_STAMP, "w") as f:
         f.write(_fingerprint())
     return LIB_PATH

@@ -440,11 +440,7 @@ extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float
   const int Tpad = (T + 31) & ~31;
   const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 4) + RA_QT * D + RA_QT * RA_MAXW + 2 * RA_MAXW * D + (size_t)RA_QT * Tpad);
   ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_relpos_attention: T=%d too long for the score buffer", T);
-  static bool attr = false;
-  if (!attr) {
-    ASB_CUDA(cudaFuncSetAttribute(relpos_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  ASB_SMEM_OPT_IN(200 * 1024, relpos_attention_kernel<128>);
   dim3 grid((T + RA_QT - 1) / RA_QT, H, B);
   ASB_CUDA(launch_k(relpos_attention_kernel<128>, grid, RA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream), 
       qkv, qkv_ld, emb_rel_k, emb_rel_v, window, T, H, lens, out, out_dtype, out_ld));
@@ -465,11 +461,7 @@ extern "C" int as_conformer_attention(const float* q, const float* k, const floa
   {
     const size_t smem_t = sizeof(float) * ((size_t)(2 * CT_QT + 1) * D + 32 * (D + 4) + (size_t)(2 * CT_QT + 1) * Tpad);
     if (smem_t <= 200 * 1024) {
-      static bool attr_t = false;
-      if (!attr_t) {
-        ASB_CUDA(cudaFuncSetAttribute(conformer_attention_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_t = true;
-      }
+      ASB_SMEM_OPT_IN(200 * 1024, conformer_attention_tiled_kernel<64>);
       dim3 grid((T + CT_QT - 1) / CT_QT, H, B);
       ASB_CUDA(launch_k(conformer_attention_tiled_kernel<64>, grid, CT_WARPS * 32, smem_t, reinterpret_cast<cudaStream_t>(stream), 
           q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld));
@@ -479,11 +471,7 @@ extern "C" int as_conformer_attention(const float* q, const float* k, const floa
   }
   const size_t smem = sizeof(float) * (size_t)CA_WARPS * (3 * D + Tpad);
   ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_conformer_attention: T=%d too long", T);
-  static bool attr = false;
-  if (!attr) {
-    ASB_CUDA(cudaFuncSetAttribute(conformer_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  ASB_SMEM_OPT_IN(200 * 1024, conformer_attention_kernel<64>);
   dim3 grid((T + CA_WARPS - 1) / CA_WARPS, H, B);
   ASB_CUDA(launch_k(conformer_attention_kernel<64>, grid, CA_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream), 
       q, k, v, qkv_ld, pos, u_bias, v_bias, T, H, lens, out, out_dtype, out_ld));

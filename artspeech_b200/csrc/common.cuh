@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/artspeech_b200.h"
 
 namespace asb {
@@ -26,6 +28,22 @@ int  check_arch();                                  // AS_OK iff current device 
 #define ASB_REQUIRE(cond, code, ...)                                        \
   do {                                                                      \
     if (!(cond)) { ::asb::set_error(__VA_ARGS__); return (code); }          \
+  } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE, so the "already done"
+// flag is a bit per device ordinal (a process may drive several GPUs, from several threads): one relaxed load on
+// the hot path, the attribute call once per (kernel, device).  Usage: ASB_SMEM_OPT_IN(bytes, kernel<template args>).
+#define ASB_SMEM_OPT_IN(bytes, ...)                                                                         \
+  do {                                                                                                      \
+    static std::atomic<unsigned long long> _asb_done[4];                                                    \
+    int _asb_dev = 0;                                                                                       \
+    ASB_CUDA(cudaGetDevice(&_asb_dev));                                                                     \
+    const unsigned long long _asb_bit = 1ull << (_asb_dev & 63);                                            \
+    std::atomic<unsigned long long>& _asb_w = _asb_done[(_asb_dev >> 6) & 3];                               \
+    if (!(_asb_w.load(std::memory_order_acquire) & _asb_bit)) {                                             \
+      ASB_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));    \
+      _asb_w.fetch_or(_asb_bit, std::memory_order_release);                                                 \
+    }                                                                                                       \
   } while (0)
 
 // ---- programmatic dependent launch (PDL) ----

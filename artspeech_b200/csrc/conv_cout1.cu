@@ -199,12 +199,8 @@ int conv_cout1_launch(const as_conv_params* p, cudaStream_t st) {
   if (!no_mma && (p->Cin % 16) == 0 && p->ntaps <= 8) {
     const int mrows = (C1M_ROWS + (p->ntaps - 1) * dil + 15) & ~15;
     const size_t msmem = (size_t)mrows * (p->Cin * 2 + 16) + (size_t)mrows * C1M_PP * sizeof(float);
-    static bool mattr = false;
-    if (!mattr) {
-      ASB_CUDA(cudaFuncSetAttribute(conv_cout1_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-      ASB_CUDA(cudaFuncSetAttribute(conv_cout1_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-      mattr = true;
-    }
+    ASB_SMEM_OPT_IN(120 * 1024, conv_cout1_mma_kernel<true>);
+    ASB_SMEM_OPT_IN(120 * 1024, conv_cout1_mma_kernel<false>);
     dim3 mgrid((unsigned)((p->T + C1M_ROWS - 1) / C1M_ROWS), (unsigned)p->B);
     const long long wts = (long long)p->CoutP * p->CinP;
     if (p->x_dtype == AS_BF16)
@@ -220,12 +216,8 @@ int conv_cout1_launch(const as_conv_params* p, cudaStream_t st) {
   }
   const int nrows = C1_ROWS + (p->ntaps - 1) * dil;
   const size_t smem = (size_t)nrows * p->Cin * 2 + (size_t)p->ntaps * p->Cin * 4;
-  static bool attr = false;
-  if (!attr) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_cout1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    ASB_CUDA(cudaFuncSetAttribute(conv_cout1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
-  }
+  ASB_SMEM_OPT_IN(160 * 1024, conv_cout1_kernel<true>);
+  ASB_SMEM_OPT_IN(160 * 1024, conv_cout1_kernel<false>);
   dim3 grid((unsigned)((p->T + C1_ROWS - 1) / C1_ROWS), (unsigned)p->B);
   const long long w_tap_stride = (long long)p->CoutP * p->CinP;    // row 0 (the only output channel) of every tap
   if (p->x_dtype == AS_BF16)

@@ -1004,12 +1004,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const EpiMaps& e
   a.stages = stages;
   const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
                       (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, BF16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ASB_SMEM_OPT_IN(227 * 1024, conv_igemm_kernel<BN, BK, BF16>);
   int grid = num_sms() * ctas_per_sm;
   if (grid > total_tiles) grid = total_tiles;
   ASB_CUDA(launch_k(conv_igemm_kernel<BN, BK, BF16>, grid, CV_THREADS, smem, st, tmA, tmW, em, a));
@@ -1029,11 +1024,7 @@ int launch_conv_2cta(const CUtensorMap& tmA, const CUtensorMap& tmWh, const EpiM
   a.idesc = (a.idesc & ~(0x1Fu << 24)) | (uint32_t(256 >> 4) << 24);      // UMMA M = 256 across the CTA pair
   const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
                       (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_igemm_2cta_kernel<BK, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ASB_SMEM_OPT_IN(227 * 1024, conv_igemm_2cta_kernel<BK, BF16>);
   const int m_tiles = a.B * a.n_ttiles * a.n_ftiles;
   const int total_super = ((m_tiles + 1) / 2) * (a.CoutP / BN);
   int clusters = num_sms() / 2;
@@ -1080,11 +1071,7 @@ int launch_halo(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeT
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo W) failed: %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ASB_SMEM_OPT_IN(227 * 1024, conv_halo_kernel<BN, BF16>);
   const int total_tiles = p->B * a.n_ttiles;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
@@ -1137,11 +1124,7 @@ int launch_halo_sw(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, Enco
                      BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ASB_REQUIRE(r == CUDA_SUCCESS, AS_ERR_CUDA, "cuTensorMapEncodeTiled(halo-sw W) failed: %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(conv_halo_sw_kernel<BN, BKC, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ASB_SMEM_OPT_IN(227 * 1024, conv_halo_sw_kernel<BN, BKC, BF16>);
   const int total_tiles = p->B * a.n_ttiles;
   int per_sm = (int)((226 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;

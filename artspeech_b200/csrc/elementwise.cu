@@ -1469,11 +1469,7 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
         const bool mx = slope >= 0.f && slope <= 1.f;
 #define ADR_LAUNCH(UP_, MX_)                                                                                                    \
   do {                                                                                                                          \
-    static bool attr = false;                                                                                                   \
-    if (!attr) {                                                                                                                \
-      ASB_CUDA(cudaFuncSetAttribute(adain_ring_kernel<UP_, MX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024));     \
-      attr = true;                                                                                                              \
-    }                                                                                                                           \
+    ASB_SMEM_OPT_IN(217 * 1024, adain_ring_kernel<UP_, MX_>);                                                                   \
     ASB_CUDA(launch_k(adain_ring_kernel<UP_, MX_>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld, \
                       eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));                                            \
   } while (0)
@@ -1496,12 +1492,8 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
         const size_t slab_bytes = (size_t)nbox * BR * 128;
         const size_t smem = slab_bytes + 128;
-        static bool attr = false;
-        if (!attr) {
-          ASB_CUDA(cudaFuncSetAttribute(adain_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-          ASB_CUDA(cudaFuncSetAttribute(adain_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-          attr = true;
-        }
+        ASB_SMEM_OPT_IN(225 * 1024, adain_tma_kernel<true>);
+        ASB_SMEM_OPT_IN(225 * 1024, adain_tma_kernel<false>);
         dim3 grid(cdiv(C, 32), (unsigned)B);
         if (up_w) ASB_CUDA(launch_k(adain_tma_kernel<true>, grid, 256, smem, ST(stream), tmx, T, BR, nbox, C, gb, gb_ld, eps, slope, lens, up_w, up_b,
                                                                          out, out_dtype, out_ld, stats));
@@ -1519,12 +1511,7 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
     dim3 grid(cdiv(C, 32) * ADF_CS, (unsigned)B);
 #define ADF_LAUNCH(UP_, XDT_)                                                                                  \
   do {                                                                                                         \
-    static bool attr = false;                                                                                  \
-    if (!attr) {                                                                                               \
-      ASB_CUDA(cudaFuncSetAttribute(adain_fused_kernel<UP_, XDT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    ADF_MAX_TR * 32 * 4));                                                      \
-      attr = true;                                                                                             \
-    }                                                                                                          \
+    ASB_SMEM_OPT_IN(ADF_MAX_TR * 32 * 4, adain_fused_kernel<UP_, XDT_>);                                       \
     ASB_CUDA(launch_k(adain_fused_kernel<UP_, XDT_>, grid, 256, smem, ST(stream), x, x_ld, T, TR, C, gb, gb_ld, eps, slope, lens, up_w, \
                                                                    up_b, out, out_dtype, out_ld, stats));       \
   } while (0)

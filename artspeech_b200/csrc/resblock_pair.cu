@@ -458,11 +458,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
 
 template <int C, bool BF16>
 static int launch_pair(const PairMaps& maps, const PairArgs& a, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASB_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ASB_SMEM_OPT_IN(227 * 1024, resblock_pair_kernel<C, BF16>);
   int grid = num_sms();
   static const int grid_cap = getenv("ASB_PAIR_GRID") ? atoi(getenv("ASB_PAIR_GRID")) : 0;   // experiments: leave SMs to concurrent streams
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;

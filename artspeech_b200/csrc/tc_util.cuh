@@ -159,12 +159,16 @@ inline EncodeTiledFn get_encode_fn() {
 extern int g_sm_limit;   // api.cu: as_set_sm_limit()
 
 inline int num_sms_device() {
-  static int n = 0;
+  // per device ordinal (a process may drive several GPUs); 0 = not queried yet
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -2,8 +2,8 @@
 
 ``Synthesizer`` owns an ``ArtsSpeech`` (second stage) and a vocoder ``Generator`` on one GPU and
 runs ``tokens + reference mel -> mel -> waveform`` for a batch of utterances, each with batch-1
-semantics.  With host-side lengths and durations the whole pass has no host synchronisation and is
-captured into a CUDA graph per shape signature (launch-bound otherwise: ~600 kernels per step).
+semantics.  The pass is replayed from CUDA graphs keyed on shape buckets, with tokens, reference mels, lengths and
+durations as graph inputs (launch-bound otherwise: ~600 kernels per step); see ``Synthesizer``.
 
 Multi-GPU: utterances are independent; ``shard_utterances`` assigns them to ranks
 longest-first (LPT) and ``gather_waveforms`` collects the results on rank 0 over NCCL — the only
@@ -11,11 +11,11 @@ collective on the path.
 """
 from __future__ import annotations
 
+import os
+from collections import OrderedDict
 from typing import List, Optional, Sequence
 
 import torch
-
-import os
 
 from . import _lib, ops
 
@@ -23,17 +23,55 @@ SAMPLE_RATE = 24000
 HOP = 300
 
 
+def _ceil_to(v: int, q: int) -> int:
+    return (int(v) + q - 1) // q * q
+
+
+class _Captured:
+    """One captured CUDA graph with its static inputs / outputs (all owned by the graph's memory pool)."""
+    __slots__ = ("graph", "tok", "mels", "voice", "meta", "dur", "lens_t", "pin_meta", "pin_free", "out", "launches",
+                 "state", "uid")
+
+    def __init__(self):
+        self.graph = self.tok = self.mels = self.voice = self.meta = self.dur = self.lens_t = None
+        self.pin_meta = self.pin_free = self.out = self.state = None
+        self.launches = 0
+        self.uid = 0
+
+
 class Synthesizer:
-    """``pipeline_depth`` > 1 keeps that many calls in flight: call ``i`` runs on side stream ``i % depth``
-    with its own CUDA-graph instance and buffers, so the latency-bound acoustic model of one batch
-    overlaps the throughput-bound vocoder of the previous one.  The outputs of a pipelined call are
-    produced on ``last_stream``: consume them there (``with torch.cuda.stream(syn.last_stream)``) or
-    after ``join()``, which makes the current stream wait for every call issued so far.
+    """Text -> waveform for batches of utterances on one GPU.
+
+    **Graph replay for real traffic.**  A pass is ~600 small launches, so it is replayed from CUDA graphs.  A graph is
+    keyed on a *shape bucket* only -- ``(B, tokens rounded up to token_quantum, reference frames, half-rate frames
+    rounded up to frame_quantum)`` -- never on the data: tokens, reference mels, token lengths and **durations are graph
+    inputs**, copied into static device buffers before each replay (one pinned staging copy carries durations and
+    lengths).  Every kernel on the path takes per-utterance lengths, so a bucket serves any mix of lengths below its
+    bounds with batch-1 semantics per utterance.  The cache is an LRU of at most ``max_graphs`` graphs per pipeline
+    slot sharing one memory pool per slot (the default ``frame_quantum`` of 40 half-rate frames = 80 mel frames makes
+    the buckets whole seconds of audio); a bucket is captured the ``capture_after``-th time it is seen and runs
+    eagerly before that.
+
+    **Durations.**  ``durations=None``: the duration predictor runs on the device (graph A: encoders + predictor +
+    ``round().clamp(min=1)``), the host reads back B integers (the utterances' frame counts, the only device->host
+    synchronisation of the pass; the reference does 2*Tt+1, models.py:362-366), picks the frame bucket and replays
+    graph B (length regulator -> predictors -> decoder -> vocoder).  ``durations=`` given (north_star: "durations
+    are fed from the reference's integer output"): one graph, no synchronisation; with ``predict_durations=True``
+    the predictor still runs inside that graph (its output is returned in ``last["duration"]`` /
+    ``last["pred_dur"]``) while the given durations drive the length regulator.
+
+    ``pipeline_depth`` > 1 keeps that many calls in flight: call ``i`` runs on side stream ``i % depth`` with its own
+    graph instances and buffers, so the latency-bound acoustic model of one batch overlaps the throughput-bound
+    vocoder of the previous one.  The outputs of a call are produced on ``last_stream``: consume them there (``with
+    torch.cuda.stream(syn.last_stream)``) or after ``join()``.  **Aliasing:** on the graph path the returned tensors
+    are views of the graph's static output buffers -- they stay valid until the next call that lands in the same
+    slot *and* bucket; enqueue the copy that consumes them (on ``last_stream``) before making that call.
     ``pcm16=True`` returns int16 samples (``rint(32767 * wav)``, the on-disk format of ``soundfile.write`` at
     test.py:119) written directly by the vocoder's last kernel: half the device->host bytes per utterance."""
 
     def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True, pipeline_depth: int = 1,
-                 pcm16: bool = False, acoustic_sms: Optional[int] = None):
+                 pcm16: bool = False, acoustic_sms: Optional[int] = None, token_quantum: int = 32,
+                 frame_quantum: int = 40, max_graphs: int = 48, capture_after: int = 1):
         self.device = torch.device(device)
         self.pcm16 = bool(pcm16)
         # SM split between the two phases when batches overlap: the acoustic model's persistent kernels are sized
@@ -42,16 +80,23 @@ class Synthesizer:
         env = os.environ.get("ASB_ACOUSTIC_SMS")
         self.acoustic_sms = int(env) if env is not None else (acoustic_sms or 0)
         self.pipeline_depth = max(1, int(pipeline_depth))
+        self.token_quantum, self.frame_quantum = max(1, int(token_quantum)), max(1, int(frame_quantum))
+        self.max_graphs, self.capture_after = max(1, int(max_graphs)), max(1, int(capture_after))
         self._slot_streams = None
         self._slot_done = {}
         self._calls = 0
         self.last_stream = None
+        self.last = {}
         self.model = model.to(self.device).eval()
         self.model.distribution = {k: v.to(self.device) for k, v in self.model.distribution.items()}
         self.generator = generator.to(self.device).eval()
         self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}
+        self._graphs = [OrderedDict() for _ in range(self.pipeline_depth)]     # per slot: key -> _Captured (LRU)
+        self._pools = [None] * self.pipeline_depth
+        self._seen = {}
+        self._uid = 0
         self.launches_per_call = None
+        self.stats = {"captures": 0, "replays": 0, "eager": 0, "evictions": 0}
 
     # ---------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -63,101 +108,246 @@ class Synthesizer:
         return tuple(self.model.style_encoder(mels, mel_lens.to(self.device), "second", self.model.distribution,
                                               host_lengths=ml))
 
-    def _forward(self, tokens, tok_lens, mels, mel_lens, durations, host_meta=None, voice=None):
-        split = self.acoustic_sms if self.pipeline_depth > 1 else 0
-        lib = _lib.load()
-        total = torch.cuda.get_device_properties(self.device).multi_processor_count
-        try:
-            if split:
-                lib.as_set_sm_limit(split)
-            mel, aux = self.model([tokens, tok_lens, mels, mel_lens], step="test", durations=durations, return_aux=True,
-                                  host_meta=host_meta, voice=voice)
-            if split:
-                lib.as_set_sm_limit(max(2, total - split))
-            wav = self.generator(mel, aux["mel_lengths"], pcm16=self.pcm16)
-        finally:
-            if split:
-                lib.as_set_sm_limit(0)
-        return wav.view(wav.shape[0], -1), aux["mel_lengths"], mel
+    # -- the two phases (models.ArtsSpeech.encode / decode + the vocoder) ---------------------------------------
+    def _sm_limit(self, n):
+        if self.acoustic_sms and self.pipeline_depth > 1:
+            _lib.load().as_set_sm_limit(n)
 
+    def _phase_a(self, tok, lens_t, mels, mel_lens_dev, host_mel_lens, voice, predict):
+        self._sm_limit(self.acoustic_sms)
+        try:
+            return self.model.encode(tok, lens_t, mels, mel_lens_dev, host_mel_lens, voice, predict)
+        finally:
+            self._sm_limit(0)
+
+    def _phase_b(self, st, dur, Lmax):
+        total = torch.cuda.get_device_properties(self.device).multi_processor_count
+        gen = self.generator
+        try:
+            self._sm_limit(self.acoustic_sms)
+            mel_cl, aux = self.model.decode(st, dur, Lmax, mel16_dtype=gen.compute_dtype)
+            self._sm_limit(max(2, total - self.acoustic_sms))
+            wav = gen.forward_channels_last(aux["mel16"], aux["mel_lengths"],
+                                            torch.int16 if self.pcm16 else torch.float32)
+        finally:
+            self._sm_limit(0)
+        mel = ops.to_channels_first(mel_cl, torch.float32)
+        return dict(wav=wav.view(wav.shape[0], -1), mel_lengths=aux["mel_lengths"], mel=mel,
+                    duration=st["duration"], pred_dur=st["pred_dur"])
+
+    def _eager(self, tokens, tl, mels, ml, durations, voice, predict):
+        """No graph: ragged reference mels, ``use_cuda_graph=False`` or a bucket not captured yet."""
+        dev = self.device
+        self.stats["eager"] += 1
+        tokens = tokens.to(dev, non_blocking=True)
+        mels = mels.to(dev, non_blocking=True)
+        lens_t = torch.tensor(tl, dtype=torch.int32).to(dev, non_blocking=True)
+        mel_lens_dev = torch.tensor(ml, dtype=torch.int64).to(dev, non_blocking=True)
+        st = self._phase_a(tokens, lens_t, mels, mel_lens_dev, ml, voice, predict or durations is None)
+        if durations is None:
+            dur = st["pred_dur"]
+            sums = [int(v) for v in st["pred_sum"].tolist()]                       # the one host sync
+        else:
+            dur = durations.to(torch.int32).to(dev, non_blocking=True).contiguous()
+            sums = [int(durations[b, :tl[b]].sum()) for b in range(len(tl))]
+        out = self._phase_b(st, dur, max(sums))
+        self.last = dict(out, frames=[2 * v for v in sums], graph=False)
+        return out["wav"], out["mel_lengths"], out["mel"]
+
+    # -- graph cache --------------------------------------------------------------------------------------------
+    def _lookup(self, slot, key):
+        cache = self._graphs[slot]
+        ent = cache.get(key)
+        if ent is not None:
+            cache.move_to_end(key)
+        return ent
+
+    def _insert(self, slot, key, ent):
+        cache = self._graphs[slot]
+        cache[key] = ent
+        while len(cache) > self.max_graphs:
+            # least recently used graph of this slot; its replays were issued on the slot's stream, wait for them
+            (self._slot_streams[slot] if self._slot_streams else torch.cuda.current_stream(self.device)).synchronize()
+            old_key, old = cache.popitem(last=False)
+            self.stats["evictions"] += 1
+            for k in [k for k, v in cache.items() if v.state is old]:          # B graphs reading an evicted A graph
+                del cache[k]
+            del old
+
+    def _capture(self, slot, fn):
+        """Warm up ``fn`` once on a side stream (weight packing, shared-memory opt-ins, allocator), then capture it
+        into the slot's memory pool.  Returns (graph, outputs, launches)."""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            fn()
+        cur.wait_stream(s)
+        torch.cuda.synchronize(dev)
+        if self._pools[slot] is None:
+            self._pools[slot] = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        before = ops.launch_count
+        with torch.cuda.graph(g, pool=self._pools[slot]):
+            out = fn()
+        self.stats["captures"] += 1
+        return g, out, ops.launch_count - before
+
+    def _static_inputs(self, B, Tt_b, mels, voice):
+        dev = self.device
+        ent = _Captured()
+        self._uid += 1
+        ent.uid = self._uid
+        ent.tok = torch.zeros(B, Tt_b, dtype=torch.int64, device=dev)
+        ent.mels = torch.zeros(tuple(mels.shape), dtype=torch.float32, device=dev)
+        ent.voice = None if voice is None else tuple(torch.zeros_like(v, device=dev) for v in voice)
+        ent.meta = torch.zeros(B * Tt_b + B, dtype=torch.int32, device=dev)
+        ent.meta[B * Tt_b:] = 1                                                # valid lengths for the warm-up pass
+        ent.dur = ent.meta[:B * Tt_b].view(B, Tt_b)
+        ent.dur[:, 0] = 1
+        ent.lens_t = ent.meta[B * Tt_b:]
+        ent.pin_meta = torch.zeros(B * Tt_b + B, dtype=torch.int32).pin_memory()
+        ent.pin_free = torch.cuda.Event()
+        return ent
+
+    def _stage(self, ent, tokens, tl, mels, durations, voice, run_stream):
+        """Refresh the graph's inputs (on ``run_stream``): tokens, reference mels / voice, and -- through ONE pinned
+        staging buffer -- the zero-padded durations and the token lengths."""
+        B, Tt_b = ent.tok.shape
+        Tt = tokens.shape[1]
+        ent.pin_free.synchronize()                      # the previous replay's copy has read the staging buffer
+        pm = ent.pin_meta
+        pd = pm[:B * Tt_b].view(B, Tt_b)
+        if durations is not None:
+            pd.zero_()
+            pd[:, :Tt] = durations
+        pm[B * Tt_b:] = torch.as_tensor(tl, dtype=torch.int32)
+        if durations is not None:
+            ent.meta.copy_(pm, non_blocking=True)
+        else:
+            ent.lens_t.copy_(pm[B * Tt_b:], non_blocking=True)
+        ent.pin_free.record(run_stream)
+        ent.tok[:, :Tt].copy_(tokens, non_blocking=True)
+        if Tt < Tt_b:
+            ent.tok[:, Tt:].zero_()
+        if ent.voice is None:
+            ent.mels.copy_(mels, non_blocking=True)
+        else:
+            for dst, src in zip(ent.voice, voice):
+                dst.copy_(src, non_blocking=True)
+
+    # ---------------------------------------------------------------------------------------
     @torch.no_grad()
-    def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None, voice=None):
-        """``tokens`` int64 [B,Tt] (device), ``tok_lens`` / ``mel_lens`` int64 [B] (HOST tensors keep the
-        pass sync-free), ``mels`` fp32 [B,80,Tr] (device), ``durations`` int64 [B,Tt] (HOST) or None
-        (use the duration predictor; costs one device->host sync).  ``voice``: cached ``encode_voice`` result
-        (the style encoder is then skipped).
-        Returns (wav fp32 [B, 300*Tm_max], mel_lengths int32 [B] (device), mel fp32 [B,80,Tm_max])."""
-        self.last_stream = torch.cuda.current_stream(self.device)
-        host_side = durations is not None and not durations.is_cuda and not tok_lens.is_cuda and not mel_lens.is_cuda
-        if not host_side:
-            return self._forward(tokens, tok_lens, mels, mel_lens, durations, voice=voice)
-        tl, ml = [int(v) for v in tok_lens.tolist()], [int(v) for v in mel_lens.tolist()]
-        Lmax = max(int(durations[b, :tl[b]].sum()) for b in range(len(tl)))
-        meta = {"mel_lens": ml, "Lmax": Lmax}
-        graphable = self.use_cuda_graph and all(v == mels.shape[2] for v in ml)
+    def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None, voice=None, predict_durations: bool = False):
+        """``tokens`` int64 [B,Tt] and ``mels`` fp32 [B,80,Tr]: device tensors or (pinned) HOST tensors -- host inputs
+        are copied straight into the graph's static buffers; ``tok_lens`` / ``mel_lens`` int64 [B] HOST tensors (or
+        lists); ``durations`` int64 [B,Tt] HOST tensor or None (predict them, one device->host sync of B integers);
+        ``voice``: cached ``encode_voice`` result (the style encoder is then skipped).
+        Returns (wav [B, 300*Tm_max] fp32 or int16, mel_lengths int32 [B] (device), mel fp32 [B,80,Tm_max]) with
+        ``Tm_max`` the longest utterance's frame count; per-call extras (predicted durations, frame counts) are in
+        ``self.last``."""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        self.last_stream = cur
+        if torch.is_tensor(tok_lens) and tok_lens.is_cuda or torch.is_tensor(mel_lens) and mel_lens.is_cuda or \
+                (durations is not None and durations.is_cuda):
+            raise ValueError("synthesize: tok_lens / mel_lens / durations are host-side metadata (CPU tensors or "
+                             "lists); device copies would force a synchronisation per call")
+        tl = [int(v) for v in (tok_lens.tolist() if torch.is_tensor(tok_lens) else tok_lens)]
+        ml = [int(v) for v in (mel_lens.tolist() if torch.is_tensor(mel_lens) else mel_lens)]
+        B, Tt = tokens.shape
+        Tr = mels.shape[2]
+        predict = bool(predict_durations) or durations is None
+        Tt_b = _ceil_to(Tt, self.token_quantum)
+        sums = None
+        if durations is not None:
+            sums = [int(durations[b, :tl[b]].sum()) for b in range(B)]
+        graphable = self.use_cuda_graph and all(v == Tr for v in ml)
+        key_a = ("ab" if durations is not None else "a", voice is not None, B, Tt_b, Tr, predict,
+                 _ceil_to(max(sums), self.frame_quantum) if sums is not None else 0)
+        if graphable:
+            n = self._seen.get(key_a, 0) + 1
+            self._seen[key_a] = n
+            graphable = n >= self.capture_after
         if not graphable:
-            return self._forward(tokens, tok_lens.to(self.device), mels, mel_lens.to(self.device),
-                                 durations.to(self.device), meta, voice=voice)
-        slot = 0
-        cur = torch.cuda.current_stream(self.device)
-        run_stream = cur
+            return self._eager(tokens, tl, mels, ml, durations, voice, predict)
+
+        slot, run_stream = 0, cur
         if self.pipeline_depth > 1:
             if self._slot_streams is None:
-                self._slot_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.pipeline_depth)]
+                self._slot_streams = [torch.cuda.Stream(device=dev) for _ in range(self.pipeline_depth)]
             slot = self._calls % self.pipeline_depth
             run_stream = self._slot_streams[slot]
         self._calls += 1
-        key = (slot, voice is not None, tuple(tokens.shape), tuple(mels.shape), tuple(tl), tuple(ml),
-               hash(durations.numpy().tobytes()))
-        entry = self._graphs.get(key)
-        if entry is None:
-            static_tok = tokens.clone()
-            static_mel = mels.clone()
-            static_voice = None if voice is None else tuple(v.clone() for v in voice)
-            tok_lens, mel_lens = tok_lens.to(self.device), mel_lens.to(self.device)
-            durations = durations.to(self.device)
-            # warm-up on a side stream (weight packing, cudaFuncSetAttribute, allocator)
-            s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta, voice=static_voice)
-            cur.wait_stream(s)
-            torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            before = ops.launch_count
-            with torch.cuda.graph(g):
-                out = self._forward(static_tok, tok_lens, static_mel, mel_lens, durations, meta, voice=static_voice)
-            self.launches_per_call = ops.launch_count - before
-            # the captured kernels read these device tensors on every replay: keep them alive with the graph
-            entry = (g, static_tok, static_mel, out, (tok_lens, mel_lens, durations), static_voice)
-            self._graphs[key] = entry
-        g, static_tok, static_mel, out, _keepalive, static_voice = entry
+
+        ent = self._lookup(slot, key_a)
+        if ent is None:
+            ent = self._static_inputs(B, Tt_b, mels, voice)
+            mel_lens_dev = torch.full((B,), Tr, dtype=torch.int64, device=dev)
+            if durations is not None:
+                L_b = key_a[-1]
+
+                def fn(ent=ent):
+                    st = self._phase_a(ent.tok, ent.lens_t, ent.mels, mel_lens_dev, ml, ent.voice, predict)
+                    return self._phase_b(st, ent.dur, L_b)
+            else:
+                def fn(ent=ent):
+                    return self._phase_a(ent.tok, ent.lens_t, ent.mels, mel_lens_dev, ml, ent.voice, True)
+            ent.graph, ent.out, ent.launches = self._capture(slot, fn)
+            if durations is None:
+                ent.state = ent.out
+                ent.out = None
+                ent.pin_meta = torch.zeros(B * Tt_b + B, dtype=torch.int32).pin_memory()
+            self._insert(slot, key_a, ent)
+
         if run_stream is not cur:
             # the slot's stream picks up after whatever produced the inputs on the caller's stream;
             # the caller's stream never waits for the slot (that would serialise the pipeline)
             ready = torch.cuda.Event()
             ready.record(cur)
             run_stream.wait_event(ready)
-            tokens.record_stream(run_stream)
-            mels.record_stream(run_stream)
-            for v in (voice or ()):
-                v.record_stream(run_stream)
+            for t in (tokens, mels) + tuple(voice or ()):
+                if t.is_cuda:
+                    t.record_stream(run_stream)
+        launches = ent.launches
         with torch.cuda.stream(run_stream):
-            static_tok.copy_(tokens, non_blocking=True)
-            if static_voice is None:
-                static_mel.copy_(mels, non_blocking=True)
+            self._stage(ent, tokens, tl, mels, durations, voice, run_stream)
+            ent.graph.replay()
+            if durations is None:
+                # the only device->host hand-off of the pass: B frame counts (the other slot keeps the GPU busy)
+                pin_sum = ent.pin_meta[:B]
+                pin_sum.copy_(ent.state["pred_sum"], non_blocking=True)
+                got = torch.cuda.Event()
+                got.record(run_stream)
+                got.synchronize()
+                sums = [int(v) for v in pin_sum.tolist()]
+                L_b = _ceil_to(max(sums), self.frame_quantum)
+                key_b = ("b", ent.uid, L_b)
+                eb = self._lookup(slot, key_b)
+                if eb is None:
+                    eb = _Captured()
+                    eb.state = ent
+                    st = ent.state
+                    eb.graph, eb.out, eb.launches = self._capture(slot, lambda: self._phase_b(st, st["pred_dur"], L_b))
+                    self._insert(slot, key_b, eb)
+                eb.graph.replay()
+                launches += eb.launches
+                out = eb.out
             else:
-                for dst, src in zip(static_voice, voice):
-                    dst.copy_(src, non_blocking=True)
-            g.replay()
+                out = ent.out
             if run_stream is not cur:
                 done = torch.cuda.Event()
                 done.record(run_stream)
                 self._slot_done[slot] = done
+        self.stats["replays"] += 1
         self.last_stream = run_stream
-        ops._count(self.launches_per_call)
-        return out
+        self.launches_per_call = launches
+        ops._count(launches)
+        Tm = 2 * max(sums)
+        self.last = dict(out, frames=[2 * v for v in sums], graph=True,
+                         duration=(ent.state or ent.out)["duration"], pred_dur=(ent.state or ent.out)["pred_dur"])
+        return out["wav"][:, :HOP * Tm], out["mel_lengths"], out["mel"][:, :, :Tm]
 
     def join(self):
         """Make the current stream wait for every pipelined call issued so far."""
@@ -181,18 +371,21 @@ def shard_utterances(costs: Sequence[float], world_size: int) -> List[List[int]]
     return shards
 
 
-def bucket_utterances(frames: Sequence[int], max_batch: int = 16, max_padded_frames: Optional[int] = None) -> List[List[int]]:
+def bucket_utterances(frames: Sequence[int], max_batch: int = 16, max_padded_frames: Optional[int] = None,
+                      quantum: int = 1) -> List[List[int]]:
     """Length-bucketed micro-batches for a mixed-length shard: utterances sorted by frame count,
     longest first, cut into runs of at most ``max_batch`` whose PADDED size ``len(run) * max(frames in run)`` stays
     within ``max_padded_frames`` -- neighbours in the sorted order have similar lengths, so padding stays small and
     every micro-batch costs about the same.  Every index appears exactly once; a single utterance longer than the
-    budget gets a micro-batch of its own."""
+    budget gets a micro-batch of its own.  ``quantum`` rounds frame counts up first (the engine's shape buckets), so
+    the batch size is a function of the bucket and repeated traffic maps onto a small set of graph keys."""
     order = sorted(range(len(frames)), key=lambda i: (-int(frames[i]), i))
     batches: List[List[int]] = []
     cur: List[int] = []
     cur_max = 0
+    q = max(1, int(quantum))
     for i in order:
-        f = max(int(frames[i]), 1)
+        f = (max(int(frames[i]), 1) + q - 1) // q * q
         longest = max(cur_max, f)
         over = max_padded_frames is not None and cur and (len(cur) + 1) * longest > max_padded_frames
         if cur and (len(cur) >= max_batch or over):
@@ -205,42 +398,121 @@ def bucket_utterances(frames: Sequence[int], max_batch: int = 16, max_padded_fra
     return batches
 
 
+class HostArena:
+    """Growable pinned host buffer the waveforms of a ``synthesize_many`` call are copied into (one 2-D
+    device->host copy per micro-batch).  Pinned allocations are slow, so the arena is kept and reused."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, n: int, dtype: torch.dtype) -> torch.Tensor:
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory()
+        return self.buf[:nbytes].view(dtype)
+
+
 @torch.no_grad()
 def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels: Sequence[torch.Tensor],
-                    durations: Sequence[torch.Tensor], max_batch: int = 16, max_padded_frames: Optional[int] = 25600):
+                    durations: Optional[Sequence[torch.Tensor]] = None, max_batch: int = 16,
+                    max_padded_frames: Optional[int] = 25600, to_host: bool = False, arena: Optional[HostArena] = None,
+                    frames_per_token: float = 5.34):
     """Mixed-length utterances through ``syn`` in length-bucketed ragged micro-batches (BASELINE config 5).
 
-    ``tokens[i]`` int64 [Tt_i], ``ref_mels[i]`` fp32 [80, Tr_i], ``durations[i]`` int64 [Tt_i] (host tensors).
-    Returns ``(wavs, frames)``: ``wavs[i]`` is a device tensor with the ``300 * frames[i]`` samples of utterance
-    ``i`` (fp32, or int16 when ``syn.pcm16``), independent of what it was batched with (batch-1 semantics)."""
+    ``tokens[i]`` int64 [Tt_i], ``ref_mels[i]`` fp32 [80, Tr_i], ``durations[i]`` int64 [Tt_i] (host tensors) or
+    ``durations=None`` to predict them (micro-batches are then formed by token count, ``frames_per_token`` being
+    the planning estimate).  Micro-batch shapes are quantised to the engine's buckets, so repeated traffic replays a
+    bounded set of CUDA graphs.  Returns ``(wavs, frames)``: ``wavs[i]`` holds the ``300 * frames[i]`` samples of
+    utterance ``i`` (fp32, or int16 when ``syn.pcm16``), independent of what it was batched with (batch-1
+    semantics) -- device tensors, or views of the pinned ``arena`` when ``to_host`` (valid after this function
+    returns: it synchronises the copies)."""
     n = len(tokens)
-    frames = [2 * int(d.sum()) for d in durations]
+    if durations is not None:
+        plan_frames = [2 * int(d.sum()) for d in durations]
+    else:
+        plan_frames = [int(round(frames_per_token * int(t.shape[0]))) for t in tokens]
+    frames: List[int] = list(plan_frames)
     wavs: List[Optional[torch.Tensor]] = [None] * n
-    for idx in bucket_utterances(frames, max_batch, max_padded_frames):
+    dt = torch.int16 if syn.pcm16 else torch.float32
+    arena = arena or (HostArena() if to_host else None)
+    host = None
+    if to_host:
+        # predicted durations: the frame counts are not known yet, reserve by the plan with head-room
+        cap = sum(plan_frames) if durations is not None else int(sum(plan_frames) * 2 + 64 * n)
+        host = arena.get(HOP * cap, dt)
+    used = 0
+    pending = []
+    for idx in bucket_utterances(plan_frames, max_batch, max_padded_frames, quantum=2 * syn.frame_quantum):
         Tt = max(int(tokens[i].shape[0]) for i in idx)
         Tr = max(int(ref_mels[i].shape[1]) for i in idx)
-        tok = torch.zeros(len(idx), Tt, dtype=torch.long)
-        dur = torch.zeros(len(idx), Tt, dtype=torch.long)
-        mel = torch.zeros(len(idx), ref_mels[idx[0]].shape[0], Tr)
+        tok = torch.zeros(len(idx), Tt, dtype=torch.long).pin_memory()
+        dur = torch.zeros(len(idx), Tt, dtype=torch.long) if durations is not None else None
+        mel = torch.zeros(len(idx), ref_mels[idx[0]].shape[0], Tr).pin_memory()
         for j, i in enumerate(idx):
             tok[j, :tokens[i].shape[0]] = tokens[i]
-            dur[j, :durations[i].shape[0]] = durations[i]
+            if dur is not None:
+                dur[j, :durations[i].shape[0]] = durations[i]
             mel[j, :, :ref_mels[i].shape[1]] = ref_mels[i]
-        tl = torch.tensor([int(tokens[i].shape[0]) for i in idx])
-        ml = torch.tensor([int(ref_mels[i].shape[1]) for i in idx])
-        wav, _, _ = syn.synthesize(tok.to(syn.device, non_blocking=True), tl, mel.to(syn.device, non_blocking=True), ml, dur)
+        tl = [int(tokens[i].shape[0]) for i in idx]
+        ml = [int(ref_mels[i].shape[1]) for i in idx]
+        wav, _, _ = syn.synthesize(tok, tl, mel, ml, dur)
+        got = syn.last["frames"]
         for j, i in enumerate(idx):
-            wavs[i] = wav[j, :HOP * frames[i]].clone()
+            frames[i] = got[j]
+        with torch.cuda.stream(syn.last_stream):
+            if to_host:
+                S = wav.shape[1]
+                if used + len(idx) * S > host.numel():
+                    raise RuntimeError("synthesize_many: host arena too small for the predicted durations")
+                dst = host[used:used + len(idx) * S].view(len(idx), S)
+                dst.copy_(wav, non_blocking=True)
+                for j, i in enumerate(idx):
+                    wavs[i] = dst[j, :HOP * frames[i]]
+                used += len(idx) * S
+            else:
+                for j, i in enumerate(idx):
+                    wavs[i] = wav[j, :HOP * frames[i]].clone()
+        pending.append((tok, mel))            # pinned inputs must outlive their asynchronous copies
+    syn.join()
+    if to_host:
+        torch.cuda.current_stream(syn.device).synchronize()
     return wavs, frames
 
 
-def gather_waveforms(wav: torch.Tensor, lengths: torch.Tensor, dst: int = 0, group=None, shapes=None):
-    """Gather per-rank ``wav`` [B_r, S_r] (+ sample ``lengths`` [B_r]) on ``dst``.
+def _as_bytes(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous().view(-1).view(torch.uint8)
 
-    Ranks may hold different batch sizes / paddings: sizes are all-gathered first, payloads are
-    padded to the common maximum for one ``gather``.  ``shapes`` (list of ``(B_r, S_r)`` per rank, known on
-    the host — e.g. from ``shard_utterances``) skips that exchange and its host synchronisation, which keeps
-    a pipelined engine asynchronous.  Works with NCCL (GPU) and gloo (CPU tests).
+
+def _pack_payload(wav: torch.Tensor, lengths: torch.Tensor, Bm: int, Sm: int, out: Optional[torch.Tensor] = None):
+    """One byte buffer per rank: ``Bm`` int64 sample counts (header) followed by the ``[Bm, Sm]`` samples.  int16 PCM
+    and fp32 both travel as bytes (the NCCL process group has no int16)."""
+    es = wav.element_size()
+    nbytes = 8 * Bm + Bm * Sm * es
+    if out is None:
+        out = torch.zeros(nbytes, dtype=torch.uint8, device=wav.device)
+    head = out[:8 * Bm].view(torch.int64)
+    head.zero_()
+    head[:lengths.shape[0]] = lengths.to(torch.int64)
+    body = out[8 * Bm:].view(wav.dtype).view(Bm, Sm)
+    if tuple(wav.shape) != (Bm, Sm):
+        body.zero_()
+    body[:wav.shape[0], :wav.shape[1]].copy_(wav)
+    return out
+
+
+def _unpack_payload(buf: torch.Tensor, dtype: torch.dtype, Bm: int, Sm: int, shape):
+    head = buf[:8 * Bm].view(torch.int64)
+    body = buf[8 * Bm:].view(dtype).view(Bm, Sm)
+    return body[:shape[0], :shape[1]], head[:shape[0]]
+
+
+def gather_waveforms(wav: torch.Tensor, lengths: torch.Tensor, dst: int = 0, group=None, shapes=None):
+    """Gather per-rank ``wav`` [B_r, S_r] (fp32 or int16 PCM) + sample ``lengths`` [B_r] on ``dst`` with ONE
+    collective: each rank contributes one byte buffer (lengths header + samples, padded to the common maximum).
+
+    Ranks may hold different batch sizes / paddings: sizes are all-gathered first unless ``shapes`` (list of
+    ``(B_r, S_r)`` per rank, known on the host -- e.g. from ``shard_utterances``) is given, which skips that
+    exchange and its host synchronisation.  Works with NCCL (GPU) and gloo (CPU tests).
     Returns (list of [B_r, S_r] tensors, list of lengths) on ``dst``, (None, None) elsewhere."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -254,20 +526,76 @@ def gather_waveforms(wav: torch.Tensor, lengths: torch.Tensor, dst: int = 0, gro
         shapes = [tuple(int(v) for v in s) for s in shapes]
         assert len(shapes) == world and shapes[rank] == tuple(wav.shape)
     Bm, Sm = max(s[0] for s in shapes), max(s[1] for s in shapes)
-    if tuple(wav.shape) == (Bm, Sm) and wav.is_contiguous():
-        pad = wav
-    else:
-        pad = torch.zeros(Bm, Sm, dtype=wav.dtype, device=wav.device)
-        pad[:wav.shape[0], :wav.shape[1]] = wav
-    lpad = torch.zeros(Bm, dtype=torch.int64, device=wav.device)
-    lpad[:lengths.shape[0]] = lengths.to(torch.int64)
-    if rank == dst:
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        lbufs = [torch.empty_like(lpad) for _ in range(world)]
-    else:
-        bufs = lbufs = None
-    dist.gather(pad, bufs, dst=dst, group=group)
-    dist.gather(lpad, lbufs, dst=dst, group=group)
+    mine = _pack_payload(wav, lengths, Bm, Sm)
+    bufs = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, bufs, dst=dst, group=group)
     if rank != dst:
         return None, None
-    return ([b[:s[0], :s[1]] for b, s in zip(bufs, shapes)], [l[:s[0]] for l, s in zip(lbufs, shapes)])
+    parts = [_unpack_payload(b, wav.dtype, Bm, Sm, s) for b, s in zip(bufs, shapes)]
+    return [p[0] for p in parts], [p[1] for p in parts]
+
+
+class WaveformGatherer:
+    """The same single-collective gather, off the critical path of a pipelined engine: ``submit`` packs the
+    rank's waveforms into a ring buffer on the producer's stream (one device copy) and issues the gather on a
+    dedicated communication stream, so neither the engine's streams nor the host wait for NCCL; ``results`` makes
+    the caller's stream wait for the most recent gather.  Every rank also keeps (and can copy out) its own
+    waveforms, so the gather is optional for serving -- it exists because north_star asks for the waveforms on one
+    rank.  ``shapes``: ``(B_r, S_r)`` per rank, fixed for the gatherer's lifetime."""
+
+    def __init__(self, device, shapes, dtype: torch.dtype, dst: int = 0, group=None, depth: int = 3):
+        import torch.distributed as dist
+        self.dist, self.group, self.dst = dist, group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.shapes = [tuple(int(v) for v in s) for s in shapes]
+        assert len(self.shapes) == self.world
+        self.dtype = dtype
+        self.Bm, self.Sm = max(s[0] for s in self.shapes), max(s[1] for s in self.shapes)
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        nbytes = 8 * self.Bm + self.Bm * self.Sm * torch.empty((), dtype=dtype).element_size()
+        self.ring = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(depth)]
+        self.recv = [[torch.empty_like(self.ring[0]) for _ in range(self.world)] if self.rank == dst else None
+                     for _ in range(depth)]
+        self.free = [None] * depth            # event: the gather that read ring[i] has finished
+        self.comm = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.n = 0
+        self.last = None
+
+    def submit(self, wav: torch.Tensor, lengths: torch.Tensor, producer_stream=None):
+        i = self.n % len(self.ring)
+        self.n += 1
+        assert tuple(wav.shape) == self.shapes[self.rank]
+        if not self.cuda:
+            _pack_payload(wav, lengths, self.Bm, self.Sm, out=self.ring[i])
+            self.dist.gather(self.ring[i], self.recv[i], dst=self.dst, group=self.group)
+            self.last = i
+            return
+        ps = producer_stream or torch.cuda.current_stream(self.device)
+        if self.free[i] is not None:
+            ps.wait_event(self.free[i])
+        with torch.cuda.stream(ps):
+            _pack_payload(wav, lengths, self.Bm, self.Sm, out=self.ring[i])
+            packed = torch.cuda.Event()
+            packed.record(ps)
+        self.comm.wait_event(packed)
+        with torch.cuda.stream(self.comm):
+            # the process group orders the collective after the current (= communication) stream and makes only
+            # that stream wait for it
+            self.dist.gather(self.ring[i], self.recv[i], dst=self.dst, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.comm)
+        self.free[i] = done
+        self.last = i
+
+    def results(self):
+        """(waveforms per rank, sample counts per rank) of the latest ``submit`` on ``dst`` (the current stream waits
+        for the gather); (None, None) elsewhere."""
+        if self.last is None:
+            return None, None
+        if self.cuda and self.free[self.last] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.free[self.last])
+        if self.rank != self.dst:
+            return None, None
+        parts = [_unpack_payload(b, self.dtype, self.Bm, self.Sm, s) for b, s in zip(self.recv[self.last], self.shapes)]
+        return [p[0] for p in parts], [p[1] for p in parts]

@@ -253,12 +253,18 @@ class DurationPredictor(nn_util.PlanMixin, nn.Module):
                                             self.duration_proj.linear_layer.bias, dt, device))
 
     @torch.no_grad()
-    def forward(self, texts, style, text_lengths, mel_input_length, host_mel_lengths=None):
+    def encode_text(self, texts, text_lengths):
+        """The predictor's own text encoder (models.py:546): independent of the style, so callers may run it
+        beside the other encoders and hand the result to ``forward(d_text=)``."""
+        self.text_encoder.compute_dtype = self.compute_dtype
+        return self.text_encoder(texts, text_lengths, want_16bit=False)
+
+    @torch.no_grad()
+    def forward(self, texts, style, text_lengths, mel_input_length, host_mel_lengths=None, d_text=None):
         """``texts`` [B,Tt], ``style`` = normalised EMA [B,10,Tr] -> duration fp32 [B,Tt]
         (models.py:540-566).  Every utterance's dur_block sees its full padded EMA row, as the
         reference's per-utterance loop does (:543-545)."""
         dev, dt = texts.device, self.compute_dtype
-        self.text_encoder.compute_dtype = dt
         p = self.plan(dev)
         B, Tt = texts.shape
         lens = _i32(text_lengths, dev)
@@ -281,7 +287,7 @@ class DurationPredictor(nn_util.PlanMixin, nn.Module):
             else:
                 dstyle[idx] = ds.view(len(idx), -1)
         gbs = StyleFC.run(p["fc"], dstyle.contiguous())
-        x, _ = self.text_encoder(texts, text_lengths, want_16bit=False), None
+        x = d_text if d_text is not None else self.encode_text(texts, text_lengths)
         rd = self.res_dtype
         for i, bp in enumerate(p["blocks"]):
             last = i == len(p["blocks"]) - 1
@@ -345,9 +351,10 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
         return p
 
     @torch.no_grad()
-    def forward_cl(self, a16: torch.Tensor, style16: torch.Tensor, lens):
+    def forward_cl(self, a16: torch.Tensor, style16: torch.Tensor, lens, lens_up=None):
         """``a16`` [B,L,512] (length-regulated arts-encoder output, ``res_dtype``), ``style16`` [B,512] ->
-        (F0 [B,2L,1], N [B,2L,1], EMA [B,2L,10]) fp32 channels-last, lens*2."""
+        (F0 [B,2L,1], N [B,2L,1], EMA [B,2L,10]) fp32 channels-last, lens*2 (``lens_up``: that tensor when the
+        caller already has it)."""
         p = self.plan(a16.device)
         dt = self.compute_dtype
         if style16.dtype != dt:                         # only when a caller mixes compute dtypes
@@ -363,7 +370,7 @@ class ArtsPredictor(nn_util.PlanMixin, nn.Module):
                 # blocks 1, 2 have a learned 1x1 shortcut (512->256->128): they need a 16-bit copy of
                 # their input; the last block's 16-bit copy is the LSTM projection's operand
                 y, y16, l = run_adain_block(blk, y, gbs[g + 2 * j], gbs[g + 2 * j + 1], l, dt, res_dtype=rd,
-                                            x16=y16, out16=dt if need16 else None)
+                                            x16=y16, out16=dt if need16 else None, lens_up=lens_up)
             xproj, _ = ops.conv(y16 if need16 else y, bp["lstm_proj"], raw=torch.float32)
             h16 = ops.bilstm(xproj, bp["whh_t"], self.d_hid // 4, l, dt)
             o, _ = ops.conv(h16, bp["out"], raw=torch.float32, lens=l)
@@ -438,9 +445,12 @@ class Decoder(nn_util.PlanMixin, nn.Module):
         return torch.empty(B, Tm, W, dtype=self.res_dtype, device=device), cat16
 
     @torch.no_grad()
-    def forward_cl(self, cat_res: torch.Tensor, cat16: torch.Tensor, style16, f0_cl, n_cl, ema_cl, lens):
+    def forward_cl(self, cat_res: torch.Tensor, cat16: torch.Tensor, style16, f0_cl, n_cl, ema_cl, lens,
+                   mel16_dtype=None):
         """``cat_res`` / ``cat16`` from ``alloc_inputs`` with channels [0,512) filled; F0/N/EMA fp32
-        channels-last [B,Tm,{1,1,10}].  Returns mel fp32 [B,Tm,80] (zeros beyond ``lens``).
+        channels-last [B,Tm,{1,1,10}].  Returns mel fp32 [B,Tm,80] (zeros beyond ``lens``); with ``mel16_dtype``
+        ``(mel, mel16)`` where ``mel16`` is the same tensor in that 16-bit dtype (the vocoder's operand), written
+        by the same launch.
 
         Everything that feeds an InstanceNorm stays in ``res_dtype`` (fp32 by default): several
         concat channels (bias-dominated F0/N/EMA features) have |mean| >> std, so a 16-bit copy of
@@ -480,8 +490,8 @@ class Decoder(nn_util.PlanMixin, nn.Module):
                                             out16=dt if (last and need16) else None)
         if need16:
             x = x16
-        mel, _ = ops.conv(x, p["to_out"], raw=torch.float32, lens=lens)
-        return mel
+        mel, mel16 = ops.conv(x, p["to_out"], raw=torch.float32, act_out=mel16_dtype, lens=lens)
+        return mel if mel16_dtype is None else (mel, mel16)
 
     @torch.no_grad()
     def forward(self, asr, Style, F0, N, EMA):
@@ -525,74 +535,144 @@ class ArtsSpeech(nn.Module):
             if isinstance(m, nn_util.PlanMixin):
                 m.invalidate_plan()
 
+    # -- phase A: everything that does not depend on the durations -------------------------------------------
     @torch.no_grad()
-    def forward(self, batch, s2s_attn=None, s2s_attn_mono=None, step="test", mode="train", epoch=0,
-                durations: Optional[torch.Tensor] = None, return_aux: bool = False, host_meta: Optional[dict] = None,
-                voice: Optional[tuple] = None):
-        """``host_meta`` (optional, keeps the pass free of device->host syncs so it can be captured in
-        a CUDA graph): ``{"mel_lens": [int], "Lmax": int}`` = reference-mel lengths and the largest
-        ``sum(durations[b, :len_b])``; requires ``durations``.
-        ``voice`` (optional): ``(f0, n, ema, Style)`` as returned by the style encoder for these utterances'
-        reference recordings; skips the style encoder (``mels`` is then only used for its shape)."""
-        if step != "test":
-            raise NotImplementedError("artspeech_b200 accelerates the synthesis path (step='test'); the "
-                                      "training branches (models.py:291-354) stay with the reference")
-        if self.stage == "first":
-            raise RuntimeError("step='test' needs a second-stage model (arts_encoder / predictors)")
-        texts, input_lengths, mels, mel_input_length = batch[0], batch[1], batch[2], batch[3]
-        dev, dt = texts.device, self.compute_dtype
-        B, Tt = texts.shape
-        lens_t = _i32(input_lengths, dev)
+    def encode(self, texts, lens_t, mels, mel_input_length, host_mel_lens=None, voice=None,
+               predict_durations: bool = True):
+        """Text / arts / style encoders (models.py:357-359) and, when ``predict_durations``, the duration
+        predictor with its device-side ``round().clamp(min=1)`` (:360-361).  ``lens_t`` int32 [B] on the device.
+        Returns the state ``decode`` consumes; no host synchronisation when ``host_mel_lens`` is given."""
+        dev = texts.device
+        dp = self.durationPredictor
+        branches = [lambda: self.text_encoder(texts, lens_t),                                     # [B,Tt,512] fp32 (:357)
+                    lambda: self.arts_encoder(texts, lens_t)]                                     # (:358)
+        if predict_durations:
+            # the predictor's own 2-layer text encoder (:546) needs only the tokens: it runs beside the others,
+            # the rest of the predictor waits for the style encoder's EMA track
+            branches.append(lambda: dp.encode_text(texts, lens_t))
+        if voice is None:
+            branches.append(lambda: self.style_encoder(mels, mel_input_length, "second", self.distribution,
+                                                       host_lengths=host_mel_lens))              # (:359)
+        res = ops.run_concurrently(branches, dev)
+        T_en, A_en = res[0], res[1]
+        # ``voice``: style-encoder outputs of the reference voice computed earlier (engine.Synthesizer.encode_voice):
+        # the 30 GFLOP style encoder runs once per voice instead of once per utterance (SURVEY.md §8f)
+        f0_ext, n_ext, ema_ext, style = voice if voice is not None else res[-1]
+        st = dict(T_en=T_en, A_en=A_en, style=style, f0_ext=f0_ext, n_ext=n_ext, ema_ext=ema_ext, lens_t=lens_t,
+                  duration=None, pred_dur=None, pred_sum=None)
+        if predict_durations:
+            duration = dp(texts, ema_ext, lens_t, mel_input_length, host_mel_lengths=host_mel_lens, d_text=res[2])
+            st["duration"] = duration                                                             # (:360)
+            st["pred_dur"], st["pred_sum"] = ops.round_durations(duration, lens_t)                # (:361) on the device
+        return st
 
-        hm = host_meta or {}
-        # the two text encoders and the style encoder are independent (:357-359): run them on
-        # concurrent streams (each is a latency-bound chain of small kernels)
-        if voice is not None:
-            # style-encoder outputs of the reference voice computed earlier (engine.Synthesizer.encode_voice):
-            # the 30 GFLOP style encoder runs once per voice instead of once per utterance (SURVEY.md §8f)
-            f0_ext, n_ext, ema_ext, style = voice
-            T_en, A_en = ops.run_concurrently([lambda: self.text_encoder(texts, input_lengths),
-                                               lambda: self.arts_encoder(texts, input_lengths)], dev)
-        else:
-            T_en, A_en, (f0_ext, n_ext, ema_ext, style) = ops.run_concurrently([
-                lambda: self.text_encoder(texts, input_lengths),                             # [B,Tt,512] fp32 (:357)
-                lambda: self.arts_encoder(texts, input_lengths),                             # (:358)
-                lambda: self.style_encoder(mels, mel_input_length, "second", self.distribution,
-                                           host_lengths=hm.get("mel_lens"))], dev)           # (:359)
-        if durations is None:
-            duration = self.durationPredictor(texts, ema_ext, input_lengths, mel_input_length,
-                                              host_mel_lengths=hm.get("mel_lens"))                # (:360)
-            pred_dur = torch.round(duration).clamp(min=1)                                # half-to-even (:361)
-        else:
-            duration = None
-            pred_dur = durations.to(dev)
-        dur = pred_dur.to(torch.int32).contiguous()
-        if dur.dim() == 1:
-            dur = dur.view(1, -1)
-        if "Lmax" in hm and durations is not None:
-            Lmax = int(hm["Lmax"])
-        else:
-            valid = torch.arange(Tt, device=dev)[None, :] < lens_t[:, None]
-            Lmax = int((dur * valid).sum(dim=1).max().item())                            # one host sync (ref: 2*Tt+1)
-        Tm = 2 * Lmax
-
-        style16 = style.to(dt).contiguous()
+    # -- phase B: length regulation -> predictors -> decoder -------------------------------------------------
+    @torch.no_grad()
+    def decode(self, st, dur, Lmax: int, mel16_dtype=None):
+        """``dur`` int32 [B,Tt] on the device (zeros or anything beyond ``lens_t``: the regulator reads
+        ``dur[b, :lens_t[b]]`` only), ``Lmax`` >= max_b sum(dur[b]) (host int; a shape bucket may round it up: the
+        extra rows come back as zeros).  Returns (mel_cl fp32 [B,2*Lmax,80], aux); ``mel16_dtype`` adds
+        ``aux["mel16"]``, the 16-bit channels-last copy the vocoder consumes."""
+        dev, dt = dur.device, self.compute_dtype
+        T_en, A_en, lens_t = st["T_en"], st["A_en"], st["lens_t"]
+        B = T_en.shape[0]
+        Tm = 2 * int(Lmax)
+        style16 = st["style"].to(dt).contiguous()
         # length regulation as a gather (the reference multiplies by a one-hot matrix, :362-368);
         # the decoder's nearest x2 upsample (:500) is fused into the same pass.
         D = self.decoder.dec_dim
-        a_reg, lens_l = ops.length_regulate(A_en, dur, lens_t, 1, Lmax, out_dtype=self.artsPredictor.res_dtype)
+        a_reg, lens_l = ops.length_regulate(A_en, dur, lens_t, 1, int(Lmax), out_dtype=self.artsPredictor.res_dtype)
         cat_res, cat16 = self.decoder.alloc_inputs(B, Tm, dev)
         _, lens_m = ops.length_regulate(T_en, dur, lens_t, 2, Tm, out=cat_res[..., :D])
         if cat16 is not cat_res:
             ops.length_regulate(T_en, dur, lens_t, 2, Tm, out=cat16[..., :D])
-        f0, n, ema, _ = self.artsPredictor.forward_cl(a_reg, style16, lens_l)            # (:369)
-        mel_cl = self.decoder.forward_cl(cat_res, cat16, style16, f0, n, ema, lens_m)    # (:370)
+        f0, n, ema, _ = self.artsPredictor.forward_cl(a_reg, style16, lens_l, lens_up=lens_m)    # (:369)
+        mel_cl = self.decoder.forward_cl(cat_res, cat16, style16, f0, n, ema, lens_m, mel16_dtype)   # (:370)
+        mel16 = None
+        if mel16_dtype is not None:
+            mel_cl, mel16 = mel_cl
+        return mel_cl, dict(mel_lengths=lens_m, F0=f0, N=n, EMA=ema, mel_cl=mel_cl, mel16=mel16)
+
+    @torch.no_grad()
+    def forward(self, batch, s2s_attn=None, s2s_attn_mono=None, step="test", mode="train", epoch=0,
+                durations: Optional[torch.Tensor] = None, return_aux: bool = False, host_meta: Optional[dict] = None,
+                voice: Optional[tuple] = None, predict_durations: Optional[bool] = None):
+        """``step="test"`` (models.py:356-371).  ``durations`` (extension): integer durations [B,Tt] used INSTEAD of
+        the predictor's (north_star: "durations are fed from the reference's integer output"); the predictor then
+        runs only if ``predict_durations`` is true (its output is returned in the aux dict, the forced durations
+        still drive the length regulator).
+        ``host_meta`` (optional, keeps the pass free of device->host syncs so it can be captured in a CUDA graph):
+        ``{"mel_lens": [int], "Lmax": int}`` = reference-mel lengths and (an upper bound of) the largest
+        ``sum(durations[b, :len_b])``; ``Lmax`` requires ``durations``.
+        ``voice`` (optional): ``(f0, n, ema, Style)`` as returned by the style encoder for these utterances'
+        reference recordings; skips the style encoder (``mels`` is then only used for its shape).
+        Training branches (``step != "test"``) are delegated to ``self.training_delegate`` (an instance of the
+        reference's own ``ArtsSpeech`` sharing this module's parameters, see ``attach_training_delegate``)."""
+        if step != "test":
+            if getattr(self, "training_delegate", None) is None:
+                raise NotImplementedError(
+                    "artspeech_b200 accelerates the synthesis path (step='test'); for the training branches "
+                    "(models.py:291-354) attach the reference module with attach_training_delegate(ref_ArtsSpeech)")
+            with torch.enable_grad():
+                return self.training_delegate(batch, s2s_attn, s2s_attn_mono, step, mode, epoch)
+        if self.stage == "first":
+            raise RuntimeError("step='test' needs a second-stage model (arts_encoder / predictors)")
+        texts, input_lengths, mels, mel_input_length = batch[0], batch[1], batch[2], batch[3]
+        dev = texts.device
+        B, Tt = texts.shape
+        lens_t = _i32(input_lengths, dev)
+        hm = host_meta or {}
+        predict = durations is None if predict_durations is None else (bool(predict_durations) or durations is None)
+        st = self.encode(texts, lens_t, mels, mel_input_length, hm.get("mel_lens"), voice, predict)
+        if durations is None:
+            dur = st["pred_dur"]
+            Lmax = int(st["pred_sum"].max().item())                                       # one host sync (ref: 2*Tt+1)
+            pred_dur = dur.to(torch.float32)                                              # what :361 returns
+        else:
+            pred_dur = durations.to(dev)
+            dur = pred_dur.to(torch.int32).contiguous()
+            if dur.dim() == 1:
+                dur = dur.view(1, -1)
+            if "Lmax" in hm:
+                Lmax = int(hm["Lmax"])
+            else:
+                valid = torch.arange(Tt, device=dev)[None, :] < lens_t[:, None]
+                Lmax = int((dur * valid).sum(dim=1).max().item())
+        mel_cl, aux = self.decode(st, dur, Lmax)
         mel = ops.to_channels_first(mel_cl, torch.float32)                               # [B,80,Tm]
         if return_aux:
-            return mel, dict(mel_lengths=lens_m, pred_dur=pred_dur, duration=duration, style=style, T_en=T_en,
-                             A_en=A_en, F0=f0, N=n, EMA=ema, f0_ext=f0_ext, n_ext=n_ext, ema_ext=ema_ext,
-                             mel_cl=mel_cl)
+            aux.update(pred_dur=pred_dur, duration=st["duration"], predicted_dur=st["pred_dur"], style=st["style"],
+                       T_en=st["T_en"], A_en=st["A_en"], f0_ext=st["f0_ext"], n_ext=st["n_ext"],
+                       ema_ext=st["ema_ext"])
+            return mel, aux
         return mel
+
+    def attach_training_delegate(self, ref_module):
+        """``ref_module``: an instance of the reference's ``models.ArtsSpeech`` (same args / stage).  Its parameters
+        and buffers are re-pointed at this module's (same ``state_dict`` keys), so optimiser steps on
+        either are seen by both; ``forward(step="first"/"second")`` then runs the reference's own PyTorch training
+        code (models.py:291-354) while ``step="test"`` stays on the CUDA path.  Call ``invalidate_plans()`` after
+        weight updates so the folded 16-bit copies are rebuilt."""
+        own_p = dict(self.named_parameters())
+        own_b = dict(self.named_buffers())
+        for name, mod in ref_module.named_modules():
+            for k in list(mod._parameters):
+                full = f"{name}.{k}" if name else k
+                if mod._parameters[k] is not None and full in own_p:
+                    if own_p[full].shape != mod._parameters[k].shape:
+                        raise ValueError(f"training delegate: shape mismatch for {full}")
+                    mod._parameters[k] = own_p[full]
+            for k in list(mod._buffers):
+                full = f"{name}.{k}" if name else k
+                if mod._buffers[k] is not None and full in own_b:
+                    mod._buffers[k] = own_b[full]
+        object.__setattr__(self, "training_delegate", ref_module)     # not a sub-module: keeps state_dict unchanged
+        return self
+
+    def invalidate_plans(self):
+        for m in self.modules():
+            if isinstance(m, nn_util.PlanMixin):
+                m.invalidate_plan()
 
 
 class _Bundle(dict):

@@ -380,6 +380,20 @@ def length_regulate(x, dur, lens_t, rep, To, out=None, out_dtype=None):
     return out, olens
 
 
+def round_durations(pred, lens_t):
+    """``pred`` fp32 [B,Tt] (the duration predictor's output) -> (dur int32 [B,Tt] = ``round(pred).clamp(min=1)``
+    for ``t < lens_t[b]`` and 0 beyond, sums int32 [B]); models.py:361 on the device."""
+    _require_cuda(pred, "round_durations")
+    B, Tt = pred.shape
+    if pred.stride(1) != 1:
+        pred = pred.contiguous()
+    dur = torch.empty(B, Tt, dtype=torch.int32, device=pred.device)
+    sums = torch.empty(B, dtype=torch.int32, device=pred.device)
+    _run("as_round_durations", pred, pred.data_ptr(), pred.stride(0), B, Tt, _p(_i32(lens_t, "round_durations")),
+         dur.data_ptr(), sums.data_ptr())
+    return dur, sums
+
+
 @dataclass
 class SmallConv:
     w: torch.Tensor            # fp32 [ntaps, Cout, Cin] device

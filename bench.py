@@ -38,18 +38,52 @@ FRAMES = 2 * SUM_DUR                                   # mel frames per utteranc
 AUDIO_S_PER_UTT = FRAMES * 300 / 24000.0               # 10.0 s
 VOCODER_FLOP_PER_FRAME = 623.7e6
 WORKLOAD = "libritts_batch16x10s_text2wave"
+N_INPUT_SETS = 8                                       # distinct (tokens, reference mels, durations) batches cycled by the timed loop
 
 
-def make_inputs(rank: int, B: int = B_PER_GPU):
-    g = torch.Generator().manual_seed(1234 + rank)
-    tokens = torch.randint(1, 178, (B, TT), generator=g)
-    mels = (torch.randn(B, 80, TR, generator=g) * 0.5).clamp(-2, 2)
-    base = SUM_DUR // TT
-    dur = torch.full((B, TT), base, dtype=torch.int64)
-    dur[:, : SUM_DUR - base * TT] += 1                 # sums to exactly 400
-    tok_lens = torch.full((B,), TT, dtype=torch.int64)
-    mel_lens = torch.full((B,), TR, dtype=torch.int64)
+def shared_config():
+    """The workload description, IDENTICAL in both arms (the driver compares the two ``config`` objects)."""
+    return {"workload": WORKLOAD, "utterances_per_gpu": B_PER_GPU, "tokens": TT, "ref_frames": TR,
+            "mel_frames": FRAMES, "audio_s_per_step_per_gpu": B_PER_GPU * AUDIO_S_PER_UTT,
+            "inputs": f"{N_INPUT_SETS} seeded input sets cycled: different tokens, reference mels and durations every step",
+            "durations": "the duration predictor runs inside every step (models.py:360); seeded integer durations "
+                         "summing to 400 per utterance drive the length regulator (north_star: durations are fed "
+                         "as integers), so every utterance is 800 frames = 10 s",
+            "weights": "random-init conditioned (seed 0); vocoder checkpoint g_00935000 not available"}
+
+
+def make_durations(g, B, Tt, total):
+    """Seeded integer durations, >= 1 per token, summing to exactly ``total`` per utterance."""
+    extra = torch.multinomial(torch.ones(B, Tt), total - Tt, replacement=True, generator=g)
+    dur = torch.ones(B, Tt, dtype=torch.int64)
+    dur.scatter_add_(1, extra, torch.ones_like(extra))
+    assert bool((dur.sum(1) == total).all()) and int(dur.min()) >= 1
+    return dur
+
+
+def make_inputs(rank: int, B: int = B_PER_GPU, set_index: int = 0, Tt: int = TT, Tr: int = TR, total: int = SUM_DUR):
+    g = torch.Generator().manual_seed(1234 + 1000 * set_index + rank)
+    tokens = torch.randint(1, 178, (B, Tt), generator=g)
+    mels = (torch.randn(B, 80, Tr, generator=g) * 0.5).clamp(-2, 2)
+    dur = make_durations(g, B, Tt, total)
+    tok_lens = torch.full((B,), Tt, dtype=torch.int64)
+    mel_lens = torch.full((B,), Tr, dtype=torch.int64)
     return tokens, tok_lens, mels, mel_lens, dur
+
+
+def make_config5(n_utts: int = 512, seed: int = 0):
+    """BASELINE config 5: seeded LibriTTS-like phoneme counts (lognormal through p50 = 125,
+    p90 = 314, clamped to 15..594), 2 or 3 half-rate frames per token (mean 2.67 -> ~5.3 mel frames per token),
+    3 s reference mels.  Same generator as round 1's tools/box_sweep.py (5 609 audio-s in total)."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    sigma = math.log(314 / 125) / 1.2816
+    tl = (125 * torch.exp(sigma * torch.randn(n_utts, generator=g))).round().clamp(15, 594).long()
+    toks = [torch.randint(1, 178, (int(t),), generator=g) for t in tl]
+    durs = [2 + (torch.rand(int(t), generator=g) < 0.67).long() for t in tl]
+    gm = torch.Generator().manual_seed(100 + seed)
+    mels = [(torch.randn(80, TR, generator=gm) * 0.5).clamp(-2, 2) for _ in range(n_utts)]
+    return toks, mels, durs
 
 
 class ClockSampler(threading.Thread):
@@ -83,15 +117,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+
+
 def vocoder_traffic():
     """DRAM bytes (read + write) of the vocoder's conv launches per step, from the committed ncu capture
-    (profiles/r01_vocoder_traffic.json); None when no capture is available."""
-    path = os.path.join(ROOT, "profiles", "r01_vocoder_traffic.json")
-    if os.path.isfile(path):
-        try:
-            return json.load(open(path)).get("dram_bytes_per_step")
-        except Exception:
-            return None
+    (profiles/r0N_vocoder_traffic.json, newest round first); None when no capture is available."""
+    for name in ("r02_vocoder_traffic.json", "r01_vocoder_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(path):
+            try:
+                return json.load(open(path)).get("dram_bytes_per_step")
+            except Exception:
+                return None
     return None
 
 
@@ -108,25 +145,32 @@ def peaks():
 # reference arm: the reference's own CPU PyTorch path (oracle/restate.py is its pinned restatement;
 # the reference tree itself does not exist on the GPU box)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_utts: int, threads: int):
-    """Time the fp32 CPU path on ``n_utts`` utterances of the bench workload (batch-1 acoustic loop,
-    as the reference's step='test' is batch-1 only; vocoder on the same utterance).  Returns
-    (audio_seconds, seconds)."""
+_CPU_STATE = {}
+
+
+def cpu_reference_sample(n_utts: int, threads: int, set_index: int = 0):
+    """Time the fp32 CPU path on ``n_utts`` utterances of the bench workload (batch-1 acoustic loop incl. the
+    duration predictor, as the reference's step='test' is batch-1 only; vocoder on the same utterance).
+    Returns (audio_seconds, seconds)."""
     from artspeech_b200 import checkpoint
     from oracle import restate
     torch.set_num_threads(threads)
-    model = checkpoint.build_random_artsspeech(0)
-    gen = checkpoint.build_random_generator(0)
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
-    gsd = {k: v.detach() for k, v in gen.state_dict().items()}
-    dist = {k: v.cpu() for k, v in model.distribution.items()}
-    tokens, _, mels, _, dur = make_inputs(0, max(n_utts, 1))
-    # warm-up on a short utterance (thread pools, oneDNN primitive caches)
-    restate.generator_forward(gsd, restate.artsspeech_test(sd, tokens[:1, :20], mels[:1, :, :100], dist,
-                                                           durations=torch.ones(20, dtype=torch.long)))
+    if not _CPU_STATE:
+        model = checkpoint.build_random_artsspeech(0)
+        gen = checkpoint.build_random_generator(0)
+        _CPU_STATE.update(sd={k: v.detach() for k, v in model.state_dict().items()},
+                          gsd={k: v.detach() for k, v in gen.state_dict().items()},
+                          dist={k: v.cpu() for k, v in model.distribution.items()})
+        # warm-up on a short utterance (thread pools, oneDNN primitive caches)
+        t, _, m, _, _ = make_inputs(0, 1)
+        restate.generator_forward(_CPU_STATE["gsd"], restate.artsspeech_test(
+            _CPU_STATE["sd"], t[:1, :20], m[:1, :, :100], _CPU_STATE["dist"], durations=torch.ones(20, dtype=torch.long),
+            predict_durations=True))
+    sd, gsd, dist = _CPU_STATE["sd"], _CPU_STATE["gsd"], _CPU_STATE["dist"]
+    tokens, _, mels, _, dur = make_inputs(0, max(n_utts, 1), set_index)
     t0 = time.perf_counter()
     for i in range(n_utts):
-        mel = restate.artsspeech_test(sd, tokens[i:i + 1], mels[i:i + 1], dist, durations=dur[i])
+        mel = restate.artsspeech_test(sd, tokens[i:i + 1], mels[i:i + 1], dist, durations=dur[i], predict_durations=True)
         wav = restate.generator_forward(gsd, mel)
         assert wav.shape[-1] == FRAMES * 300
     dt = time.perf_counter() - t0
@@ -139,24 +183,25 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     n_per_step = 2
-    for _ in range(args.warmup):
-        pass                                           # warm-up happens inside cpu_reference_sample
+    for i in range(min(args.warmup, 1)):
+        cpu_reference_sample(1, threads, i)
     times = []
     audio = 0.0
-    for _ in range(args.steps):
-        a, t = cpu_reference_sample(n_per_step, threads)
+    for i in range(args.steps):
+        a, t = cpu_reference_sample(n_per_step, threads, i % N_INPUT_SETS)
         audio += a
         times.append(t)
     total = sum(times)
     value = audio / total
+    sample = (f"{n_per_step} of the step's {B_PER_GPU} utterances per step (10 s each; the step is a batch-1 loop, so "
+              f"audio-s/s does not depend on how many are run), duration predictor + acoustic + vocoder, fp32 torch "
+              f"restatement of the reference pinned to it by tests/test_oracle_pinning.py")
     line = {"impl": "reference", "metric": "synthesized_audio_seconds_per_second", "value": value,
             "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "tokens": TT, "ref_frames": TR, "mel_frames": FRAMES,
-                       "utterances_per_step": n_per_step},
-            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                             "sample": f"{n_per_step} utterances x 10 s per step, batch-1 acoustic + vocoder, fp32 torch"},
+            "config": shared_config(),
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
@@ -165,6 +210,219 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _events():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def bench_vocoder_roofline(syn, mel_static, lens_static, dev, steps):
+    """The dominant kernel family: the vocoder's tensor-core convolutions (fused resblock-pair launches +
+    implicit-GEMM launches, nothing else), replayed from a CUDA graph (no launch gaps), CUDA events on the launch
+    stream.  Timed twice: a short burst (the kernel family alone: vs the BURST bf16 peak) and a >= 2 s loop (vs the
+    SUSTAINED peak, both from MEASURED_PEAKS.json)."""
+    from artspeech_b200 import ops
+    gen = syn.generator
+    m16 = mel_static.transpose(1, 2).to(gen.compute_dtype).contiguous()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            gen.forward_channels_last(m16, lens_static)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    vg = torch.cuda.CUDAGraph()
+    before = ops.launch_count
+    with torch.cuda.graph(vg):
+        gen.forward_channels_last(m16, lens_static)
+    launches = ops.launch_count - before
+    for _ in range(3):
+        vg.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = _events()
+    reps = max(10, steps)
+    e0.record()
+    for _ in range(reps):
+        vg.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    burst_ms = e0.elapsed_time(e1) / reps
+    long_reps = int(2200.0 / burst_ms) + 1
+    e0.record()
+    for _ in range(long_reps):
+        vg.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    long_ms = e0.elapsed_time(e1) / long_reps
+    return launches, burst_ms, long_ms, long_reps
+
+
+def bench_config1(model, gen, dev):
+    """BASELINE config 1 on the GPU: ONE utterance (120 phonemes, 3 s reference mel), latency per call with a host
+    synchronisation after each: to the mel, to the waveform (forced Σdur = 400 -> 10 s, and with predicted
+    durations: two graphs + the frame-count read-back), and time to the first audio chunk of Generator.stream()."""
+    from artspeech_b200 import engine
+    syn = engine.Synthesizer(model, gen, device=dev, pipeline_depth=1)
+    tok, tl, mel, ml, dur = make_inputs(0, 1, 0, Tt=120, total=SUM_DUR)
+    tok_p, mel_p = tok.pin_memory(), mel.pin_memory()
+    wav_h = torch.empty(1, FRAMES * 300).pin_memory()
+
+    def call(durations):
+        t0 = time.perf_counter()
+        wav, _, _ = syn.synthesize(tok_p, tl, mel_p, ml, durations, predict_durations=True)
+        n = wav.shape[1]
+        wav_h[:, :n].copy_(wav, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return (time.perf_counter() - t0) * 1e3, n
+
+    for _ in range(3):
+        call(dur)
+        call(None)
+    forced = _median([call(dur)[0] for _ in range(15)])
+    pred = [call(None) for _ in range(15)]
+    # acoustic model alone (to the mel): its own graph
+    tok_d, mel_d = tok.to(dev), mel.to(dev)
+    tl_d, ml_d, dur_d = tl.to(dev), ml.to(dev), dur.to(dev)
+    meta = {"mel_lens": [TR], "Lmax": SUM_DUR}
+    run = lambda: model([tok_d, tl_d, mel_d, ml_d], step="test", durations=dur_d, host_meta=meta, predict_durations=True)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        run()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        mel_out = run()
+    ts = []
+    for _ in range(12):
+        t0 = time.perf_counter()
+        g.replay()
+        torch.cuda.current_stream(dev).synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    to_mel = _median(ts[2:])
+    # streaming vocoder: first 64-frame chunk (+ receptive-field halo) of the mel, incl. its device->host copy
+    first = []
+    chunk_h = torch.empty(1, 1, 64 * 300).pin_memory()
+    for _ in range(8):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        _, w = next(iter(gen.stream(mel_out, chunk_frames=64)))
+        chunk_h.copy_(w, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        first.append((time.perf_counter() - t0) * 1e3)
+    return {"workload": "1 utterance, 120 phonemes, 3 s reference mel, 800 frames = 10 s (forced) / predicted",
+            "ms_to_mel": to_mel, "ms_to_waveform": forced, "audio_s_per_s": AUDIO_S_PER_UTT / (forced / 1e3),
+            "ms_to_waveform_predicted_durations": _median([p[0] for p in pred]),
+            "predicted_audio_s": pred[0][1] / 24000.0,
+            "stream_first_chunk_ms_after_mel": _median(first[2:]),
+            "time_to_first_audio_ms": to_mel + _median(first[2:]),
+            "note": "host wall-clock per call incl. H2D of the inputs, D2H of the waveform and a stream synchronise"}
+
+
+def bench_config3(gen, dev, pk):
+    """BASELINE config 3: vocoder-only sweep, mel 80 x {200, 800, 3200} frames at batch 1..64, whole Generator,
+    TFLOP/s at 623.7 MFLOP per frame, graph replay, vs the burst bf16 peak."""
+    out = {}
+    fr = []
+    for T in (200, 800, 3200):
+        for B in (1, 2, 4, 8, 16, 32, 64):
+            g0 = torch.Generator().manual_seed(0)
+            mel = torch.randn(B, T, 80, generator=g0).clamp(-2, 2).to(dev).to(gen.compute_dtype)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                gen.forward_channels_last(mel)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gen.forward_channels_last(mel)
+            g.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = _events()
+            reps = 3 if B * T >= 51200 else 10
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / reps
+            tf = VOCODER_FLOP_PER_FRAME * B * T / (ms / 1e3) / 1e12
+            out[f"{B}x{T}"] = round(tf, 1)
+            fr.append(tf / pk["bf16_tflops"])
+            del g, mel
+            torch.cuda.empty_cache()
+    fr.sort()
+    return {"tflops": out, "frac_of_burst_peak": {"min": fr[0], "median": fr[len(fr) // 2], "max": fr[-1]},
+            "note": "whole Generator (51 launches) per point; small points do not fill 148 SMs"}
+
+
+def bench_config4(syn, dev, steps=3):
+    """BASELINE config 4: 8 utterances x 60 s (900 tokens, 4800 frames), text -> waveform."""
+    sets = [make_inputs(0, 8, i, Tt=900, total=2400) for i in range(2)]
+    dsets = [(t.to(dev), tl, m.to(dev), ml, d) for t, tl, m, ml, d in sets]
+    torch.cuda.reset_peak_memory_stats(dev)
+    for i in range(4):
+        t, tl, m, ml, d = dsets[i % 2]
+        syn.synthesize(t, tl, m, ml, d, predict_durations=True)
+    syn.join()
+    torch.cuda.synchronize(dev)
+    e0, e1 = _events()
+    e0.record()
+    for i in range(steps):
+        t, tl, m, ml, d = dsets[i % 2]
+        syn.synthesize(t, tl, m, ml, d, predict_durations=True)
+    syn.join()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "8 utterances x 60 s (900 tokens, 4800 mel frames each)", "ms_per_step": ms,
+            "audio_s_per_s": 8 * 60.0 / (ms / 1e3), "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}
+
+
+def bench_config5(syn, dev, rank, world, dist, passes=2):
+    """BASELINE config 5: 512 seeded mixed-length utterances, LPT-sharded over the run's N GPUs (strong scaling),
+    each rank through engine.synthesize_many (length-bucketed micro-batches on bucketed CUDA graphs, waveforms
+    copied to pinned host memory).  Warm-up passes run until no new graph is captured; timing = max over ranks."""
+    from artspeech_b200 import engine
+    toks, mels, durs = make_config5()
+    frames = [2 * int(d.sum()) for d in durs]
+    mine = engine.shard_utterances(frames, world)[rank]
+    my_t, my_m, my_d = [toks[i] for i in mine], [mels[i] for i in mine], [durs[i] for i in mine]
+    arena = engine.HostArena()
+    for _ in range(4):
+        before = syn.stats["captures"]
+        engine.synthesize_many(syn, my_t, my_m, my_d, to_host=True, arena=arena)
+        if syn.stats["captures"] == before:
+            break
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = _events()
+    e0.record()
+    for _ in range(passes):
+        wavs, fr = engine.synthesize_many(syn, my_t, my_m, my_d, to_host=True, arena=arena)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / passes
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    audio = sum(frames) * 300 / 24000.0
+    nb = len(engine.bucket_utterances([frames[i] for i in mine], 16, 25600, quantum=2 * syn.frame_quantum))
+    return {"workload": "512 seeded mixed-length utterances (15-594 tokens), 3 s reference mels, sharded over the N GPUs",
+            "scaling": "strong", "n_gpus": world, "audio_s": audio, "ms_per_pass": ms,
+            "audio_s_per_s": audio / (ms / 1e3), "micro_batches_rank0": nb, "graphs_rank0": syn.stats["captures"],
+            "graph_replays_rank0": syn.stats["replays"], "eager_calls_rank0": syn.stats["eager"],
+            "d2h": "every rank copies its own waveforms to pinned host memory inside the timed region"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from artspeech_b200 import checkpoint, engine, ops
@@ -181,31 +439,34 @@ def run_ours(args):
 
     model = checkpoint.build_random_artsspeech(0)
     gen = checkpoint.build_random_generator(0)
-    syn = engine.Synthesizer(model, gen, device=dev, use_cuda_graph=not args.no_graph,
-                             pipeline_depth=1 if args.no_graph else args.pipeline)
+    depth = 1 if args.no_graph else args.pipeline
+    syn = engine.Synthesizer(model, gen, device=dev, use_cuda_graph=not args.no_graph, pipeline_depth=depth)
 
-    tokens, tok_lens, mels, mel_lens, dur = make_inputs(rank)
-    tok_d, mel_d = tokens.to(dev), mels.to(dev)
+    sets = [make_inputs(rank, B_PER_GPU, i) for i in range(N_INPUT_SETS)]
+    tok_lens, mel_lens = sets[0][1], sets[0][3]
+    dev_sets = [(t.to(dev), m.to(dev), d) for t, _, m, _, d in sets]
     # pinned host staging for the end-to-end arm
-    tok_h, mel_h = tokens.pin_memory(), mels.pin_memory()
-    wav_hs = [torch.empty(B_PER_GPU, FRAMES * 300, dtype=torch.float32).pin_memory() for _ in range(max(args.pipeline, 1))]
-    wav_h = wav_hs[0]
-    calls = [0]
+    host_sets = [(t.pin_memory(), m.pin_memory(), d) for t, _, m, _, d in sets]
+    wav_hs = [torch.empty(B_PER_GPU, FRAMES * 300, dtype=torch.float32).pin_memory() for _ in range(max(depth, 1) + 1)]
+    calls = [0, 0]
     wav_lens_d = torch.full((B_PER_GPU,), FRAMES * 300, device=dev)
+    gat = engine.WaveformGatherer(dev, [(B_PER_GPU, FRAMES * 300)] * world, torch.float32, dst=0) if world > 1 else None
 
     def step_resident():
-        return syn.synthesize(tok_d, tok_lens, mel_d, mel_lens, dur)
+        t, m, d = dev_sets[calls[0] % N_INPUT_SETS]
+        calls[0] += 1
+        return syn.synthesize(t, tok_lens, m, mel_lens, d, predict_durations=True)
 
     def step_e2e():
-        t = tok_h.to(dev, non_blocking=True)
-        m = mel_h.to(dev, non_blocking=True)
-        wav, _, _ = syn.synthesize(t, tok_lens, m, mel_lens, dur)
-        calls[0] += 1
-        # the waveforms are produced on the engine's stream for this call: gather / D2H follow on that stream
+        t, m, d = host_sets[calls[1] % N_INPUT_SETS]
+        calls[1] += 1
+        # pinned host tokens / mels go straight into the graph's static buffers (H2D inside the call)
+        wav, _, _ = syn.synthesize(t, tok_lens, m, mel_lens, d, predict_durations=True)
+        # the waveforms are produced on the engine's stream for this call: D2H (and the gather) follow on that stream
         with torch.cuda.stream(syn.last_stream):
-            if world > 1:
-                gathered, _ = engine.gather_waveforms(wav, wav_lens_d, shapes=[tuple(wav.shape)] * world)
-            wav_hs[calls[0] % len(wav_hs)].copy_(wav, non_blocking=True)
+            wav_hs[calls[1] % len(wav_hs)].copy_(wav, non_blocking=True)
+        if gat is not None:
+            gat.submit(wav, wav_lens_d, syn.last_stream)       # one collective, on its own stream, overlapped
         return wav
 
     def barrier():
@@ -215,11 +476,13 @@ def run_ours(args):
 
     def timed(fn, steps):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = _events()
         e0.record()
         for _ in range(steps):
             fn()
         syn.join()                 # pipelined calls run on the engine's streams: the end event waits for all of them
+        if gat is not None:
+            gat.results()          # ... and for the last gather
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -229,10 +492,12 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(max(warm, 2 * depth)):
         step_resident()
         step_e2e()
     barrier()
+    captures_after_warmup = syn.stats["captures"]
 
     # inputs (tokens 19 KB + mels 1.2 MB) are tiny, but every step streams > 10 GB of activations
     # through HBM, far beyond the 126 MB L2: no explicit flush needed between timed iterations.
@@ -244,52 +509,50 @@ def run_ours(args):
     launches = ops.launch_count - l0
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
+    assert syn.stats["captures"] == captures_after_warmup, "the timed region must replay graphs, not capture them"
 
-    # extra (not the headline): the same step with the style-encoder outputs cached per reference voice
-    # (engine.encode_voice) — the serving case where many utterances share a voice
-    voice = syn.encode_voice(mel_d, mel_lens)
+    # BASELINE config 5 on every rank (strong scaling over the run's N GPUs)
+    c5 = None
+    if not args.no_graph and not args.skip_configs:
+        syn5 = engine.Synthesizer(model, gen, device=dev, pipeline_depth=depth, max_graphs=96)
+        c5 = bench_config5(syn5, dev, rank, world, dist)
+        del syn5
+        torch.cuda.empty_cache()
 
-    def step_voice_cached():
-        return syn.synthesize(tok_d, tok_lens, mel_d, mel_lens, dur, voice=voice)
-    for _ in range(3):
-        step_voice_cached()
-    ms_cached = timed(step_voice_cached, args.steps)
+    extras = {}
+    if rank == 0 and world == 1:
+        pk = peaks()
+        e0, e1 = _events()
+        # the same step with the style-encoder outputs cached per reference voice
+        tok_d, mel_d, dur = dev_sets[0]
+        voice = syn.encode_voice(mel_d, mel_lens)
+        step_voice = lambda: syn.synthesize(tok_d, tok_lens, mel_d, mel_lens, dur, voice=voice, predict_durations=True)
+        for _ in range(2 * depth + 1):
+            step_voice()
+        ms_cached = timed(step_voice, args.steps)
+        extras["voice_cached"] = {"value": B_PER_GPU * AUDIO_S_PER_UTT * args.steps / (ms_cached / 1e3), "unit": "audio-s/s",
+                                  "ms_per_step": ms_cached / args.steps,
+                                  "note": "style-encoder outputs cached per reference voice (not the BASELINE config: informational)"}
 
-    # dominant kernel family: the vocoder's tensor-core convolutions (27 fused resblock-pair launches + 24
-    # implicit-GEMM launches, nothing else).
-    # Timed alone, replayed from a CUDA graph (no launch gaps), with CUDA events on the launch stream.
-    _, lens_m, mel_out = step_resident()
-    syn.join()
-    mel_static = mel_out.clone()
-    lens_static = lens_m.clone()
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for _ in range(2):
-            syn.generator(mel_static, lens_static)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    torch.cuda.synchronize(dev)
-    vg = torch.cuda.CUDAGraph()
-    l_before = ops.launch_count
-    with torch.cuda.graph(vg):
-        syn.generator(mel_static, lens_static)
-    voc_launches = ops.launch_count - l_before
-    for _ in range(3):
-        vg.replay()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(5, args.steps)
-    e0.record()
-    for _ in range(reps):
-        vg.replay()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    voc_ms = e0.elapsed_time(e1) / reps
-    voc_flops = VOCODER_FLOP_PER_FRAME * B_PER_GPU * FRAMES
+        _, lens_m, mel_out = step_resident()
+        syn.join()
+        torch.cuda.synchronize(dev)
+        voc_launches, voc_ms, voc_long_ms, long_reps = bench_vocoder_roofline(syn, mel_out.clone(), lens_m.clone(), dev, args.steps)
+        voc_flops = VOCODER_FLOP_PER_FRAME * B_PER_GPU * FRAMES
+        achieved = voc_flops / (voc_ms / 1e3) / 1e12
+        sustained = voc_flops / (voc_long_ms / 1e3) / 1e12
+        extras["roofline"] = {
+            "bound": "tensor", "kernel": f"resblock_pair + conv_igemm kernels (vocoder, {voc_launches} launches per step)",
+            "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+            "traffic": vocoder_traffic(),
+            "peak_source": pk["source"] + " BURST bf16 (the kernel family timed alone, graph replay, %.0f ms)" % (voc_ms * max(10, args.steps)),
+            "flops_per_step": voc_flops, "vocoder_ms": voc_ms, "vocoder_share_of_step": voc_ms / (ms / args.steps),
+            "sustained": {"achieved": sustained, "peak": pk["bf16_tflops_sustained"],
+                          "frac": sustained / pk["bf16_tflops_sustained"], "vocoder_ms": voc_long_ms,
+                          "loop_s": voc_long_ms * long_reps / 1e3,
+                          "note": "same graph replayed back to back for >= 2 s vs the sustained bf16 peak"}}
 
-    # MAS (BASELINE config 5): 64 x 200 tokens x 1000 frames, fp32, bit-exact path
-    mas_info = None
-    if rank == 0:
+        # MAS (BASELINE config 5): 64 x 200 tokens x 1000 frames, fp32, bit-exact path
         from artspeech_b200 import mas
         gm = torch.Generator().manual_seed(7)
         val = torch.randn(64, 200, 1000, generator=gm).to(dev)
@@ -307,19 +570,19 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         mas_ms = e0.elapsed_time(e1) / 20
         mas_bytes = 2.0 * 64 * 200 * 1000 * 4
-        mas_info = {"shape": "64x200x1000 fp32", "ms": mas_ms, "algorithmic_GBps": mas_bytes / mas_ms / 1e6,
-                    "frac_of_hbm_peak": mas_bytes / mas_ms / 1e6 / peaks()["hbm_gbs"],
-                    "note": "serial dependency chain over Ty: latency-bound by construction, not roofline-graded"}
+        extras["mas"] = {"shape": "64x200x1000 fp32", "ms": mas_ms, "algorithmic_GBps": mas_bytes / mas_ms / 1e6,
+                         "frac_of_hbm_peak": mas_bytes / mas_ms / 1e6 / pk["hbm_gbs"],
+                         "note": "serial dependency chain over Ty: latency-bound by construction, not roofline-graded"}
+        del val
 
-    # HBM-bound kernel family: fused InstanceNorm + AdaIN + LeakyReLU (as_adain_norm_apply) at the decoder's
-    # widest block, fp32 in -> f16 out.  Six rotating input sets (> 126 MB L2), launches replayed back to back
-    # from a CUDA graph, algorithmic bytes = one read + one write of the tensor.
-    hbm_info = None
-    if rank == 0:
+        # HBM-bound kernel family: fused InstanceNorm + AdaIN + LeakyReLU (as_adain_norm_apply) at the decoder's
+        # widest block, fp32 in -> f16 out.  Six rotating input sets (> 126 MB L2), launches replayed back to back
+        # from a CUDA graph, algorithmic bytes = one read + one write of the tensor.
         nset, Cd = 6, 1024
         xs = [torch.randn(B_PER_GPU, FRAMES, Cd, device=dev) * 0.7 + 3.0 for _ in range(nset)]
         gbv = torch.randn(B_PER_GPU, 2 * Cd, device=dev) * 0.3
         lens_f = torch.full((B_PER_GPU,), FRAMES, dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for xv in xs:
@@ -338,15 +601,14 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         ad_us = e0.elapsed_time(e1) / (5 * nset) * 1e3
         ad_bytes = B_PER_GPU * FRAMES * Cd * (4 + 2)
-        hbm_info = {"bound": "hbm", "kernel": "adain_ring_kernel (InstanceNorm + AdaIN + LeakyReLU, 16x800x1024 fp32 -> f16)",
-                    "achieved": ad_bytes / ad_us / 1e3, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
-                    "frac": ad_bytes / ad_us / 1e3 / peaks()["hbm_gbs"], "us_per_launch": ad_us,
-                    "bytes_per_launch": ad_bytes, "l2": "6 rotating input sets (474 MB), graph replay"}
-        del xs, keep
+        extras["roofline_hbm"] = {
+            "bound": "hbm", "kernel": "adain_ring_kernel (InstanceNorm + AdaIN + LeakyReLU, 16x800x1024 fp32 -> f16)",
+            "achieved": ad_bytes / ad_us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ad_bytes / ad_us / 1e3 / pk["hbm_gbs"], "us_per_launch": ad_us,
+            "bytes_per_launch": ad_bytes, "l2": "6 rotating input sets (474 MB), graph replay"}
+        del xs, keep, ag
 
-    # the step before the path: log-mel front-end of the 16 reference recordings (3 s each)
-    fe_info = None
-    if rank == 0:
+        # the step before the path: log-mel front-end of the 16 reference recordings (3 s each)
         from artspeech_b200 import frontend
         fe = frontend.LogMel().to(dev)
         wv = torch.randn(B_PER_GPU, TR * 300, device=dev) * 0.1
@@ -358,9 +620,15 @@ def run_ours(args):
             fe(wv)
         e1.record()
         torch.cuda.synchronize(dev)
-        fe_info = {"kernel": "log_mel_kernel (STFT 2048/1200/300 + 80 mel + log, fp32)", "recordings": B_PER_GPU,
-                   "seconds_each": TR * 300 / 24000.0, "us": e0.elapsed_time(e1) / 20 * 1e3,
-                   "note": "not part of the timed step (reference mels are the step's inputs, as in BASELINE configs)"}
+        extras["frontend"] = {"kernel": "log_mel_kernel (STFT 2048/1200/300 + 80 mel + log, fp32)", "recordings": B_PER_GPU,
+                              "seconds_each": TR * 300 / 24000.0, "us": e0.elapsed_time(e1) / 20 * 1e3,
+                              "note": "not part of the timed step (reference mels are the step's inputs, as in BASELINE configs)"}
+        torch.cuda.empty_cache()
+        if not args.skip_configs:
+            extras["config1"] = bench_config1(model, gen, dev)
+            extras["config3"] = bench_config3(syn.generator, dev, pk)
+            torch.cuda.empty_cache()
+            extras["config4"] = bench_config4(syn, dev)
 
     if rank != 0:
         if world > 1:
@@ -370,41 +638,35 @@ def run_ours(args):
     audio_per_step = world * B_PER_GPU * AUDIO_S_PER_UTT
     value = audio_per_step * args.steps / (ms / 1e3)
     e2e_value = audio_per_step * args.steps / (ms_e2e / 1e3)
-    pk = peaks()
-    achieved = voc_flops / (voc_ms / 1e3) / 1e12
+    t0, m0, _ = host_sets[0]
+    meta_bytes = 4 * (B_PER_GPU * ((TT + syn.token_quantum - 1) // syn.token_quantum * syn.token_quantum) + B_PER_GPU)
     line = {
         "metric": "synthesized_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 (vocoder) / f16 (acoustic) operands, f32 accumulate", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "utterances_per_gpu": B_PER_GPU, "tokens": TT, "ref_frames": TR,
-                   "mel_frames": FRAMES, "audio_s_per_step_per_gpu": B_PER_GPU * AUDIO_S_PER_UTT,
-                   "weights": "random-init conditioned (seed 0); vocoder checkpoint g_00935000 not available",
-                   "cuda_graph": not args.no_graph, "batches_in_flight": 1 if args.no_graph else args.pipeline,
-                   "l2": "activations streamed per step >> 126 MB L2, no explicit flush"},
+        "config": shared_config(),
+        "engine": {"cuda_graph": not args.no_graph, "batches_in_flight": depth,
+                   "graph_key": "shape bucket (B, tokens/32, ref frames, frames/80); tokens, mels, lengths and durations "
+                                "are graph inputs refreshed per call",
+                   "graphs_captured": captures_after_warmup, "graph_replays": syn.stats["replays"],
+                   "l2": "activations streamed per step >> 126 MB L2, no explicit flush",
+                   "multi_gpu": None if world == 1 else "every rank D2H-copies its own waveforms; one asynchronous "
+                                "NCCL gather per step to rank 0 on a communication stream (e2e arm only)"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(tok_h.numel() * 8 + mel_h.numel() * 4),
-                "d2h_bytes_per_step": int(wav_h.numel() * 4)},
+                "h2d_bytes_per_step": int(t0.numel() * 8 + m0.numel() * 4 + meta_bytes),
+                "d2h_bytes_per_step": int(wav_hs[0].numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": f"resblock_pair + conv_igemm kernels (vocoder, {voc_launches} launches per step)",
-                     "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": vocoder_traffic(),
-                     "peak_source": pk["source"] + " sustained bf16 (kernel family timed inside a long step)",
-                     "flops_per_step": voc_flops, "vocoder_ms": voc_ms,
-                     "vocoder_share_of_step": voc_ms / (ms / args.steps)},
-        "roofline_hbm": hbm_info,
-        "frontend": fe_info,
-        "voice_cached": {"value": world * B_PER_GPU * AUDIO_S_PER_UTT * args.steps / (ms_cached / 1e3), "unit": "audio-s/s",
-                         "ms_per_step": ms_cached / args.steps,
-                         "note": "style-encoder outputs cached per reference voice (not the BASELINE config: informational)"},
-        "mas": mas_info,
     }
+    line.update(extras)
+    if c5 is not None:
+        line["config5"] = c5
     if world == 1 and not args.no_cpu_baseline:
         a, t = cpu_reference_sample(args.cpu_utts, os.cpu_count() or 1)
         line["cpu_baseline"] = {"value": a / t, "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": f"{args.cpu_utts} utterances of the same workload (10 s each), batch-1 "
-                                          f"acoustic + vocoder, fp32 torch restatement of the reference"}
+                                "sample": f"{args.cpu_utts} utterances of the same workload (10 s each), batch-1 duration "
+                                          f"predictor + acoustic + vocoder, fp32 torch restatement of the reference"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -432,7 +694,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=2,
                     help="batches in flight per GPU (2: the acoustic model of step i+1 overlaps the vocoder of step i)")
-    ap.add_argument("--cpu-utts", type=int, default=4)
+    ap.add_argument("--cpu-utts", type=int, default=16, help="utterances of the CPU baseline sample (~0.6 s each on 16 cores)")
+    ap.add_argument("--skip-configs", action="store_true", help="headline + rooflines only (no config1/3/4/5 extras)")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 (NCCL prints its version banner there
     # when NCCL_DEBUG is set) are sent to stderr for the whole run, the JSON line goes to the saved descriptor

@@ -255,6 +255,14 @@ int as_length_regulate(const void* x, int32_t x_dtype, int64_t x_ld, int32_t B, 
                        int32_t To, void* out, int32_t out_dtype, int64_t out_ld,
                        int32_t* out_lens, void* stream);
 
+/* Integer durations on the device (models.py:361: pred_dur = torch.round(duration).clamp(min=1), round-half-to-even):
+ * dur[b,t] = max(1, rint(pred[b,t])) for t < lens_t[b], 0 beyond; sum[b] = sum_t dur[b,t] (half-rate frames of
+ * utterance b; may be NULL).  Keeps the predictor -> length-regulator hand-off on the device, so durations are an
+ * INPUT of the captured CUDA graph and the host reads back B integers instead of doing 2*Tt+1 syncs (models.py:362-366).
+ * pred fp32 [B,Tt] with row stride pred_ld; dur int32 [B,Tt] contiguous; sum int32 [B]. */
+int as_round_durations(const float* pred, int64_t pred_ld, int32_t B, int32_t Tt, const int32_t* lens_t,
+                       int32_t* dur, int32_t* sum, void* stream);
+
 /* Direct convolution for tiny input-channel counts (Cin <= 16) on CUDA cores: first layers of the
  * 2-D stacks (1 -> 64, 3x3), F0/N/EMA 1x1 convs of the decoder (models.py:480-482, 502-504).
  * x [B,T,F,Cin]; w fp32 [ntaps][Cout][Cin]; taps host arrays; stride 1; zero padding; outputs as

@@ -431,17 +431,20 @@ def decoder(sd, asr, style, f0, n, ema):
 
 
 @torch.no_grad()
-def artsspeech_test(sd, tokens, mel, dist, durations=None, want_aux=False):
+def artsspeech_test(sd, tokens, mel, dist, durations=None, want_aux=False, predict_durations=False):
     """ArtsSpeech.forward(step='test') (models.py:356-371) for ONE utterance:
     ``tokens`` [1,Tt], ``mel`` [1,80,Tr] -> mel [1,80,2*sum(dur)].  ``durations`` (int [Tt]) replaces
-    round(duration).clamp(min=1)."""
+    round(duration).clamp(min=1); with ``predict_durations`` the duration predictor (:360) still runs (its
+    output is returned in the aux dict) while the given durations drive the length regulation -- the
+    benchmark's step, identical in both arms."""
     lengths = torch.tensor([tokens.shape[1]])
     t_en = rel_transformer_encoder(_sub(sd, "text_encoder."), tokens, lengths, 4).transpose(1, 2)
     a_en = rel_transformer_encoder(_sub(sd, "arts_encoder."), tokens, lengths, 4).transpose(1, 2)
     f0e, ne, emae, style = style_encoder(_sub(sd, "style_encoder."), mel, dist)
     duration = None
-    if durations is None:
+    if durations is None or predict_durations:
         duration = duration_predictor(_sub(sd, "durationPredictor."), tokens, emae, lengths)
+    if durations is None:
         durations = torch.round(duration.squeeze(0)).clamp(min=1)
     idx = torch.repeat_interleave(torch.arange(tokens.shape[1]), durations.long().view(-1))   # one-hot matmul == gather
     f0, n, ema = arts_predictor(_sub(sd, "artsPredictor."), a_en[:, :, idx], style)

@@ -218,6 +218,14 @@ def length_regulate(x, dur, lens_t, rep, To, out=None, out_dtype=None):
     return out, olens
 
 
+def round_durations(pred, lens_t):
+    B, Tt = pred.shape
+    d = torch.round(pred.float()).clamp(min=1).to(torch.int32)
+    if lens_t is not None:
+        d = d * (torch.arange(Tt)[None, :] < lens_t[:, None].long()).to(torch.int32)
+    return d, d.sum(dim=1).to(torch.int32)
+
+
 def conv_small(x, sc, *, raw=None, act_out=None, act=ops.ACT_NONE, slope=0.0, lens=None):
     squeeze = x.dim() == 3
     x4 = (x.unsqueeze(2) if squeeze else x).float()
@@ -346,7 +354,7 @@ def to_channels_first(src, out_dtype, lens=None, sub=None, mul=None):
 
 
 SIM_FUNCS = ["conv", "resblock_pair", "embed", "layernorm", "relpos_attention", "conformer_attention", "instnorm_stats",
-             "adain_apply", "adain_norm", "repeat_rows", "length_regulate", "conv_small", "dwconv", "avgpool",
+             "adain_apply", "adain_norm", "repeat_rows", "length_regulate", "round_durations", "conv_small", "dwconv", "avgpool",
              "affine_act_maxpool", "global_avgpool", "bilstm", "lstm_onestep", "log_norm",
              "to_channels_last", "to_channels_first"]
 

@@ -36,6 +36,14 @@ def test_length_bucketed_micro_batches():
             assert all(len(b) == 1 or len(b) * max(frames[i] for i in b) <= budget for b in batches)
         padded = sum(len(b) * max(frames[i] for i in b) for b in batches)
         assert padded <= 1.06 * sum(frames)                  # sorted neighbours: < 6 % padding
+    # quantised frame counts (the engine's shape buckets): still a partition, the budget holds for the bucketed size,
+    # and the set of (batch size, bucket) keys is small
+    batches = engine.bucket_utterances(frames, 16, 25600, quantum=128)
+    assert sorted(i for b in batches for i in b) == list(range(512))
+    q = lambda f: (f + 127) // 128 * 128
+    assert all(len(b) == 1 or len(b) * q(max(frames[i] for i in b)) <= 25600 for b in batches)
+    keys = {(len(b), q(max(frames[i] for i in b))) for b in batches}
+    assert len(keys) <= len(batches) and sum(len(b) * q(max(frames[i] for i in b)) for b in batches) <= 1.10 * sum(frames)
     assert engine.bucket_utterances([], 16) == []
     assert engine.bucket_utterances([40000], 16, 25600) == [[0]]          # over-budget utterance: its own batch
     assert engine.bucket_utterances([10, 30, 20], 2) == [[1, 2], [0]]
@@ -67,8 +75,18 @@ def _worker(rank, world, port, q):
         shards = engine.shard_utterances(costs, world)
         shapes = [(len(sh), max([costs[i] * 3 for i in sh], default=1)) for sh in shards]
         wavs2, lns2 = engine.gather_waveforms(wav, lens, dst=0, shapes=shapes)
+        # int16 PCM payload (Synthesizer(pcm16=True)): travels as bytes, NCCL has no int16
+        wavs3, lns3 = engine.gather_waveforms(wav.to(torch.int16), lens, dst=0, shapes=shapes)
+        # the pipelined gatherer: ring buffers + one collective per submit; two submits, the second one wins
+        gat = engine.WaveformGatherer("cpu", shapes, torch.float32, dst=0)
+        gat.submit(wav * 0, lens)
+        gat.submit(wav, lens)
+        wavs4, lns4 = gat.results()
         if rank == 0:
             ok = all(torch.equal(a, b) for a, b in zip(wavs, wavs2)) and all(torch.equal(a, b) for a, b in zip(lns, lns2))
+            ok &= all(w.dtype == torch.int16 and torch.equal(w.float(), a) for w, a in zip(wavs3, wavs))
+            ok &= all(torch.equal(a, b) for a, b in zip(lns, lns3))
+            ok &= all(torch.equal(a, b) for a, b in zip(wavs, wavs4)) and all(torch.equal(a, b) for a, b in zip(lns, lns4))
             for r in range(world):
                 for row, i in enumerate(shards[r]):
                     n = int(lns[r][row])
@@ -76,7 +94,7 @@ def _worker(rank, world, port, q):
                         bool((wavs[r][row, n:] == 0).all())
             q.put(ok)
         else:
-            assert wavs is None and lns is None and wavs2 is None
+            assert wavs is None and lns is None and wavs2 is None and wavs3 is None and wavs4 is None
     finally:
         dist.destroy_process_group()
 

@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import _lib, ops
+from . import _lib, nn_util, ops
 
 SAMPLE_RATE = 24000
 HOP = 300
@@ -95,8 +95,17 @@ class Synthesizer:
         self._pools = [None] * self.pipeline_depth
         self._seen = {}
         self._uid = 0
+        self._epoch = nn_util.plan_epoch()
         self.launches_per_call = None
-        self.stats = {"captures": 0, "replays": 0, "eager": 0, "evictions": 0}
+        self.stats = {"captures": 0, "replays": 0, "eager": 0, "evictions": 0, "drops": 0}
+
+    @classmethod
+    def from_cache(cls, path: str, device="cuda:0", expect_hash: Optional[str] = None, **kw) -> "Synthesizer":
+        """Start from a converted checkpoint (``python -m artspeech_b200.convert``): the folded,
+        packed weights are read from ``path`` instead of being re-derived from the parameters in this process."""
+        from . import convert
+        model, gen = convert.load_cache(path, device, expect_hash)
+        return cls(model, gen, device=device, **kw)
 
     # ---------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -155,6 +164,17 @@ class Synthesizer:
         return out["wav"], out["mel_lengths"], out["mel"]
 
     # -- graph cache --------------------------------------------------------------------------------------------
+    def drop_graphs(self):
+        """Forget every captured graph (they bake in the addresses of the packed weights: called when a
+        ``load_state_dict`` / device move re-packed them)."""
+        torch.cuda.synchronize(self.device)
+        for cache in self._graphs:
+            cache.clear()
+        # a memory pool whose graphs are all gone cannot be captured into again: new pools for the new graphs
+        self._pools = [None] * self.pipeline_depth
+        self._epoch = nn_util.plan_epoch()
+        self.stats["drops"] += 1
+
     def _lookup(self, slot, key):
         cache = self._graphs[slot]
         ent = cache.get(key)
@@ -192,6 +212,7 @@ class Synthesizer:
         with torch.cuda.graph(g, pool=self._pools[slot]):
             out = fn()
         self.stats["captures"] += 1
+        self._epoch = nn_util.plan_epoch()          # the warm-up pass may have packed weights for the first time
         return g, out, ops.launch_count - before
 
     def _static_inputs(self, B, Tt_b, mels, voice):
@@ -272,6 +293,8 @@ class Synthesizer:
             graphable = n >= self.capture_after
         if not graphable:
             return self._eager(tokens, tl, mels, ml, durations, voice, predict)
+        if self._epoch != nn_util.plan_epoch():
+            self.drop_graphs()
 
         slot, run_stream = 0, cur
         if self.pipeline_depth > 1:
@@ -399,17 +422,30 @@ def bucket_utterances(frames: Sequence[int], max_batch: int = 16, max_padded_fra
 
 
 class HostArena:
-    """Growable pinned host buffer the waveforms of a ``synthesize_many`` call are copied into (one 2-D
-    device->host copy per micro-batch).  Pinned allocations are slow, so the arena is kept and reused."""
+    """Pinned host memory the waveforms of a ``synthesize_many`` call are copied into (one 2-D device->host copy
+    per micro-batch).  Pinned allocations are slow, so blocks are kept and handed out again after ``reset()``;
+    a request that does not fit the remaining space adds a block."""
 
-    def __init__(self):
-        self.buf = None
+    def __init__(self, block_bytes: int = 64 << 20):
+        self.block_bytes = int(block_bytes)
+        self.blocks: List[torch.Tensor] = []
+        self.cur = 0
+        self.off = 0
 
-    def get(self, n: int, dtype: torch.dtype) -> torch.Tensor:
-        nbytes = n * torch.empty((), dtype=dtype).element_size()
-        if self.buf is None or self.buf.numel() < nbytes:
-            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory()
-        return self.buf[:nbytes].view(dtype)
+    def reset(self):
+        self.cur = self.off = 0
+
+    def take(self, n: int, dtype: torch.dtype) -> torch.Tensor:
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+        while True:
+            if self.cur < len(self.blocks) and self.off + nbytes <= self.blocks[self.cur].numel():
+                out = self.blocks[self.cur][self.off:self.off + nbytes]
+                self.off += nbytes
+                return out.view(dtype)[:n]
+            if self.cur < len(self.blocks):
+                self.cur, self.off = self.cur + 1, 0
+                continue
+            self.blocks.append(torch.empty(max(nbytes, self.block_bytes), dtype=torch.uint8).pin_memory())
 
 
 @torch.no_grad()
@@ -435,12 +471,8 @@ def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels
     wavs: List[Optional[torch.Tensor]] = [None] * n
     dt = torch.int16 if syn.pcm16 else torch.float32
     arena = arena or (HostArena() if to_host else None)
-    host = None
     if to_host:
-        # predicted durations: the frame counts are not known yet, reserve by the plan with head-room
-        cap = sum(plan_frames) if durations is not None else int(sum(plan_frames) * 2 + 64 * n)
-        host = arena.get(HOP * cap, dt)
-    used = 0
+        arena.reset()
     pending = []
     for idx in bucket_utterances(plan_frames, max_batch, max_padded_frames, quantum=2 * syn.frame_quantum):
         Tt = max(int(tokens[i].shape[0]) for i in idx)
@@ -462,13 +494,10 @@ def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels
         with torch.cuda.stream(syn.last_stream):
             if to_host:
                 S = wav.shape[1]
-                if used + len(idx) * S > host.numel():
-                    raise RuntimeError("synthesize_many: host arena too small for the predicted durations")
-                dst = host[used:used + len(idx) * S].view(len(idx), S)
+                dst = arena.take(len(idx) * S, dt).view(len(idx), S)
                 dst.copy_(wav, non_blocking=True)
                 for j, i in enumerate(idx):
                     wavs[i] = dst[j, :HOP * frames[i]]
-                used += len(idx) * S
             else:
                 for j, i in enumerate(idx):
                     wavs[i] = wav[j, :HOP * frames[i]].clone()

@@ -151,25 +151,55 @@ def pack_lstm(lstm: nn.LSTM, dtype, device, in_perm: Optional[torch.Tensor] = No
     return proj, whh_t
 
 
+# Bumped whenever any module's plan is dropped.  CUDA graphs bake the addresses of the packed weights in, so the
+# engine compares this counter before replaying and re-captures when weights were re-packed meanwhile.
+_PLAN_EPOCH = [0]
+
+
+def plan_epoch() -> int:
+    return _PLAN_EPOCH[0]
+
+
+def bump_plan_epoch() -> None:
+    _PLAN_EPOCH[0] += 1
+
+
+def param_signature(module: nn.Module):
+    """Device and dtype of the module's parameters / buffers: ``.to()`` onto the device they already are on keeps
+    it.  (Addresses are deliberately not part of it: ``nn.LSTM._apply`` re-flattens its weights into a fresh cuDNN
+    buffer on every ``.to()``, while the plans hold their own packed copies.)"""
+    return tuple((t.dtype, str(t.device)) for t in list(module.parameters()) + list(module.buffers()))
+
+
 class PlanMixin:
-    """Lazy plan cache for a module tree; invalidated by load_state_dict and device moves."""
+    """Lazy plan cache for a module tree; invalidated by load_state_dict and by device / dtype moves that actually
+    move the parameters (``model.to(device)`` on a model that already lives there keeps the packed weights, which
+    captured CUDA graphs point at)."""
 
     def _init_plan(self):
         self._plan = None
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate_plan())
 
     def invalidate_plan(self):
+        if self._plan is not None:
+            bump_plan_epoch()
         self._plan = None
         for m in self.children():
             if isinstance(m, PlanMixin):
                 m.invalidate_plan()
 
     def _apply(self, fn, *a, **kw):
-        self._plan = None
-        return super()._apply(fn, *a, **kw)
+        before = param_signature(self)
+        out = super()._apply(fn, *a, **kw)
+        if param_signature(self) != before and self._plan is not None:
+            self._plan = None
+            bump_plan_epoch()
+        return out
 
     def plan(self, device):
         if self._plan is None or self._plan.get("_device") != str(device):
+            if self._plan is not None:
+                bump_plan_epoch()
             self._plan = self._build_plan(device)
             self._plan["_device"] = str(device)
         return self._plan

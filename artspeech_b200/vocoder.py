@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 from torch.nn.utils import remove_weight_norm, weight_norm
 
-from . import ops
+from . import nn_util, ops
 
 LRELU_SLOPE = 0.1
 FUSED_PAIR_CHANNELS = (32, 64, 128)      # stages run by as_hifigan_resblock_pair (one launch per conv pair)
@@ -133,11 +133,16 @@ class Generator(nn.Module):
         self.invalidate_plan()
 
     def invalidate_plan(self):
+        if self._plan is not None:
+            nn_util.bump_plan_epoch()
         self._plan = None
 
-    def _apply(self, fn, *a, **kw):  # .to()/.cuda() move parameters: re-pack lazily
-        self._plan = None
-        return super()._apply(fn, *a, **kw)
+    def _apply(self, fn, *a, **kw):  # .to()/.cuda() that really move the parameters: re-pack lazily
+        before = nn_util.param_signature(self)
+        out = super()._apply(fn, *a, **kw)
+        if nn_util.param_signature(self) != before:
+            self.invalidate_plan()
+        return out
 
     # -- weight preparation --------------------------------------------------------------------
     def _build_plan(self, device):

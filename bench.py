@@ -649,7 +649,7 @@ def run_ours(args):
         "engine": {"cuda_graph": not args.no_graph, "batches_in_flight": depth,
                    "graph_key": "shape bucket (B, tokens/32, ref frames, frames/80); tokens, mels, lengths and durations "
                                 "are graph inputs refreshed per call",
-                   "graphs_captured": captures_after_warmup, "graph_replays": syn.stats["replays"],
+                   "graphs_captured": captures_after_warmup, "stats": dict(syn.stats),
                    "l2": "activations streamed per step >> 126 MB L2, no explicit flush",
                    "multi_gpu": None if world == 1 else "every rank D2H-copies its own waveforms; one asynchronous "
                                 "NCCL gather per step to rank 0 on a communication stream (e2e arm only)"},

@@ -148,7 +148,7 @@ def test_graph_cache_is_bounded_lru(model_gpu):
         w0, _, _ = ref.synthesize(tok.to(DEV), [Tt] * B, mel.to(DEV), [Tr] * B, dur)
         assert util.snr_db(w.cpu(), w0.cpu()) >= 50.0, i
     run(0)
-    assert syn.stats == {"captures": 0, "replays": 0, "eager": 1, "evictions": 0}     # first sighting runs eagerly
+    assert syn.stats == {"captures": 0, "replays": 0, "eager": 1, "evictions": 0, "drops": 0}   # first sighting: eager
     run(0); run(1); run(1); run(2); run(2)
     assert syn.stats["captures"] == 3 and syn.stats["evictions"] == 1
     assert len(syn._graphs[0]) == 2
@@ -216,3 +216,29 @@ def test_bench_shape_against_oracle(model_gpu):
     near_tie = ((aux["duration"].view(-1) % 1.0) - 0.5).abs() < 2e-3
     assert torch.equal(got[~near_tie], want[~near_tie])
     assert (syn.last["duration"][i, :150].cpu() - aux["duration"].view(-1)).abs().max().item() < 5e-3
+
+
+def test_graphs_survive_a_second_engine_and_follow_weight_reloads(model_gpu):
+    """Captured graphs point at the packed weights.  Building another Synthesizer on the same modules
+    (``model.to(device)`` on a model that is already there) must not re-pack them; a ``load_state_dict`` does, and
+    the engine then re-captures instead of replaying graphs that read freed memory."""
+    from artspeech_b200 import engine
+    model, g, _, _ = model_gpu
+    gen = util.generator(0).to(DEV)
+    gsrc = torch.Generator().manual_seed(13)
+    tok, mel, dur = _batch(gsrc, 2, 30, 100, [30, 30])
+    syn = engine.Synthesizer(model, gen, device=DEV, use_cuda_graph=True)
+    w0, _, _ = syn.synthesize(tok.to(DEV), [30, 30], mel.to(DEV), [100, 100], dur)
+    w0 = w0.clone()
+    other = engine.Synthesizer(model, gen, device=DEV, use_cuda_graph=True)      # same modules, same device
+    other.synthesize(tok.to(DEV), [30, 30], mel.to(DEV), [100, 100], dur)
+    del other
+    torch.cuda.empty_cache()
+    w1, _, _ = syn.synthesize(tok.to(DEV), [30, 30], mel.to(DEV), [100, 100], dur)
+    assert torch.equal(w1, w0) and syn.stats["captures"] == 1
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)                                                    # re-packs the weights
+    torch.cuda.empty_cache()
+    w2, _, _ = syn.synthesize(tok.to(DEV), [30, 30], mel.to(DEV), [100, 100], dur)
+    torch.cuda.synchronize()
+    assert torch.equal(w2, w0) and syn.stats["captures"] == 2 and syn.stats["drops"] == 1

@@ -33,10 +33,23 @@ namespace asb {
 
 constexpr int RP_THREADS = 640;
 
+// Development aid (ASB_PAIR_DBG bit 5): CTA 0 records clock64() at the hand-off points of its first 32 tiles,
+// trace[event * 32 + tile]; read back with as_debug_pair_trace().  Events: 0 producer got the buffer, 1/2 stage-1
+// MMAs issue begin/end (M-tile 0), 3/4 stage-2, 5 group-1 has tile + D2 buffer, 6 seed done, 7 D1 ready, 8 group
+// synced, 9 epilogue-1 math done, 10 group-1 signalled, 11 group-2 sees D2, 12 group-2 drained, 13 x tile landed.
+__device__ unsigned long long g_pair_trace[20 * 32];
+#define RP_TRACE(ev, tile_i)                                                                          \
+  do {                                                                                                \
+    if ((a.dbg & 32) && blockIdx.x == 0 && (tile_i) < 32) g_pair_trace[(ev) * 32 + (tile_i)] = clock64(); \
+  } while (0)
+
 struct PairArgs {
   int B, L, tiles_per_item, total_tiles;
   int k, dil, p1, p2, R_out, HA, HB, tail_rows;
   int NX, ND, NSTG, SW, stream1, stream2, pipelined;
+  int NT;    // stage-2 operand buffers: 0 = written in place over the input tile, 1..2 = separate buffers (the
+             // input tile is then released as soon as stage 1 and the residual read are done)
+  int dbg;   // timing experiments only (ASB_PAIR_DBG; results are wrong): 1 no MMAs, 2 no stores, 4 no reloads, 8 no epilogue-1 math, 16 no seed
   uint32_t idesc;
   const float* b1;
   const float* b2;
@@ -68,22 +81,43 @@ __device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
   a = f.x; b = f.y;
 }
 
+// Ring position + phase parity, advanced incrementally: every role of the kernel walks its buffers once per tile, and a
+// runtime `i % n` / `i / n` costs ~100 dependent cycles each on what is a single-thread critical path (measured with
+// the hand-off trace: four of them per stage put ~450 idle cycles between two MMA batches).
+struct RingPos {
+  int idx, n;
+  uint32_t ph;
+  __device__ __forceinline__ RingPos(int n_) : idx(0), n(n_), ph(0) {}
+  __device__ __forceinline__ void next() { if (++idx == n) { idx = 0; ph ^= 1u; } }
+};
+// (item, tile-in-item) of the CTA's i-th tile, advanced by gridDim.x tiles per step
+struct TilePos {
+  int b, tt, step, per_item;
+  __device__ __forceinline__ TilePos(int first, int step_, int per_item_) : step(step_), per_item(per_item_) {
+    b = first / per_item_; tt = first - b * per_item_;
+  }
+  __device__ __forceinline__ void next() { tt += step; while (tt >= per_item) { tt -= per_item; ++b; } }
+};
+
 // shared-memory plan, computed identically on host and device
 struct PairSmem {
-  uint32_t xb, x_off, wres_off, ring_off, stg_off, bias_off, bar_off, total;
+  uint32_t xb, x_off, tb, t_off, wres_off, ring_off, stg_off, bias_off, bar_off, total;
 };
-__host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int NSTG, int SW, int stream1, int stream2) {
+constexpr uint32_t RP_NBARS = 96;
+__host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int NT, int NSTG, int SW, int stream1, int stream2) {
   const uint32_t BKC = C >= 64 ? 64 : 32, RB = BKC * 2, KCH = C / BKC, WBLK = (uint32_t)C * RB;
   PairSmem s;
   s.xb = ((KCH * (uint32_t)HA * RB) + 1023u) & ~1023u;
   s.x_off = 0;
-  s.wres_off = s.x_off + NX * s.xb;
+  s.tb = KCH * 256u * RB;                       // 256 rows of conv1 output per tile (multiple of 1024 bytes)
+  s.t_off = s.x_off + NX * s.xb;
+  s.wres_off = s.t_off + NT * s.tb;
   const uint32_t nres = (stream1 ? 0 : k * KCH) + (stream2 ? 0 : k * KCH);
   s.ring_off = s.wres_off + nres * WBLK;
   s.stg_off = s.ring_off + SW * WBLK;
   s.bias_off = s.stg_off + 8u * NSTG * 32u * RB;
   s.bar_off = s.bias_off + 2u * C * 4u;
-  s.total = s.bar_off + 8u * 64u;
+  s.total = s.bar_off + 8u * RP_NBARS;
   return s;
 }
 
@@ -100,15 +134,17 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
 
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const PairSmem sp = pair_smem(C, a.HA, a.k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2);
-  const int NX = a.NX, ND = a.ND, SW = a.SW;
+  const PairSmem sp = pair_smem(C, a.HA, a.k, a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2);
+  const int NX = a.NX, ND = a.ND, SW = a.SW, NT = a.NT;
+  const uint32_t t_chunk_bytes = 256u * RB;
   const uint32_t chunk_bytes = (uint32_t)a.HA * RB;
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (base + sp.bias_off - smem_u32(smem_dyn)));
   const uint32_t bars = base + sp.bar_off;
   // barrier map (8 bytes each)
-  auto x_full = [&](int i) { return bars + 8u * i; };            // [4]
-  auto x_empty = [&](int i) { return bars + 8u * (4 + i); };     // [4]
+  auto x_full = [&](int i) { return bars + 8u * (64 + i); };     // [8]
+  auto x_empty = [&](int i) { return bars + 8u * (72 + i); };    // [8]
   auto t_full = [&](int i) { return bars + 8u * (8 + i); };      // [4]
+  auto t_empty = [&](int i) { return bars + 8u * (80 + i); };    // [4]
   auto d1_full = [&](int i) { return bars + 8u * (12 + i); };    // [2]
   auto d1_empty = [&](int i) { return bars + 8u * (14 + i); };   // [2]
   auto d2_init = [&](int i) { return bars + 8u * (16 + i); };    // [2]
@@ -123,7 +159,9 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bias_s[i] = i < C ? a.b1[i] : a.b2[i - C];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 2); mbar_init(t_full(i), 8); }
+    // separate stage-2 buffers: the input tile is released by the two stage-1 commits + the eight residual readers
+    for (int i = 0; i < 8; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), a.NT ? 10 : 2); }
+    for (int i = 0; i < 4; ++i) { mbar_init(t_full(i), 8); mbar_init(t_empty(i), 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full(i), 2); mbar_init(d1_empty(i), 8); mbar_init(d2_init(i), 8);
       mbar_init(d2_full(i), 2); mbar_init(d2_empty(i), 8);
@@ -164,12 +202,15 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       // ===== activation-tile producer =====
-      for (int i = 0; i < n_local; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int b = tile / a.tiles_per_item, tt = tile - b * a.tiles_per_item;
-        const int xb = i % NX;
-        const uint32_t ph = (uint32_t)(i / NX) & 1u;
+      RingPos xr(NX);
+      TilePos tp(blockIdx.x, gridDim.x, a.tiles_per_item);
+      for (int i = 0; i < n_local; ++i, xr.next(), tp.next()) {
+        const int b = tp.b, tt = tp.tt;
+        const int xb = xr.idx;
+        const uint32_t ph = xr.ph;
         mbar_wait(x_empty(xb), ph ^ 1u);
+        RP_TRACE(0, i);
+        if ((a.dbg & 4) && i >= NX) { mbar_arrive(x_full(xb)); continue; }
         mbar_expect_tx(x_full(xb), (uint32_t)KCH * chunk_bytes);
         const int row0 = tt * a.R_out - a.p2 - a.p1;
         const uint32_t dst = base + sp.x_off + xb * sp.xb;
@@ -193,19 +234,28 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
             tma_load_2d(w2_res + j * WBLK, &maps.w2, wres_full, (j % KCH) * BKC, (j / KCH) * C);
       }
       if (a.stream1 || a.stream2) {
-        int g = 0;
-        for (int i = 0; i < n_local; ++i) {
-          for (int conv = 0; conv < 2; ++conv) {
-            if (!(conv == 0 ? a.stream1 : a.stream2)) continue;
-            const CUtensorMap* wm = conv == 0 ? &maps.w1 : &maps.w2;
-            for (int j = 0; j < nblk; ++j, ++g) {
-              const int slot = g % SW;
-              const uint32_t ph = (uint32_t)(g / SW) & 1u;
-              mbar_wait(wr_empty(slot), ph ^ 1u);
-              mbar_expect_tx(wr_full(slot), WBLK);
-              tma_load_2d(ring + slot * WBLK, wm, wr_full(slot), (j % KCH) * BKC, (j / KCH) * C);
-            }
+        // the ring is filled in the order the MMA issuers consume it: stage 1 and stage 2 of every tile, and in
+        // pipelined mode S1(0), then S1(i+1) before S2(i)
+        RingPos wr(SW);
+        auto feed = [&](int conv) {
+          if (!(conv == 0 ? a.stream1 : a.stream2)) return;
+          const CUtensorMap* wm = conv == 0 ? &maps.w1 : &maps.w2;
+          for (int j = 0; j < nblk; ++j, wr.next()) {
+            const int slot = wr.idx;
+            const uint32_t ph = wr.ph;
+            mbar_wait(wr_empty(slot), ph ^ 1u);
+            mbar_expect_tx(wr_full(slot), WBLK);
+            tma_load_2d(ring + slot * WBLK, wm, wr_full(slot), (j % KCH) * BKC, (j / KCH) * C);
           }
+        };
+        if (a.pipelined) {
+          if (n_local > 0) feed(0);
+          for (int i = 0; i < n_local; ++i) {
+            if (i + 1 < n_local) feed(0);
+            feed(1);
+          }
+        } else {
+          for (int i = 0; i < n_local; ++i) { feed(0); feed(1); }
         }
       }
     }
@@ -219,11 +269,12 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
       if (!a.stream1 || !a.stream2) mbar_wait(wres_full, 0);
       int slot = 0;            // weight ring position (streamed convolutions, in-order mode only)
       uint32_t slot_ph = 0;
-      const uint64_t chunk_step = (uint64_t)(chunk_bytes >> 4);
+      const uint64_t x_chunk_step = (uint64_t)(chunk_bytes >> 4), t_chunk_step = (uint64_t)(t_chunk_bytes >> 4);
       const uint32_t idesc = a.idesc;
       const int k = a.k;
+      const bool do_mma = !(a.dbg & 1);
       // one convolution of one M-tile: k taps x KCH chunks x KS instructions into accumulator `tacc`
-      auto run_conv = [&](uint32_t tacc, uint64_t da_tap, uint64_t tap_step, uint32_t w_res, bool streamed, uint32_t acc) {
+      auto run_conv = [&](uint32_t tacc, uint64_t da_tap, uint64_t tap_step, uint64_t chunk_step, uint32_t w_res, bool streamed, uint32_t acc) {
         if (!streamed) {
           uint64_t dw = make_smem_desc<BKC>(w_res);
           for (int tap = 0; tap < k; ++tap, da_tap += tap_step) {
@@ -231,7 +282,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
             for (int c = 0; c < KCH; ++c, dw += (uint64_t)(WBLK >> 4)) {
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
-                tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                if (do_mma) tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
                 acc = 1u;
               }
             }
@@ -245,7 +296,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
               const uint64_t dw = make_smem_desc<BKC>(ring + slot * WBLK);
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
-                tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                if (do_mma) tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
                 acc = 1u;
               }
               tc_commit(wr_empty(slot));
@@ -254,24 +305,38 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
           }
         }
       };
+      RingPos x1(NX), d1(ND), x2(NX), d2(ND), t2(NT ? NT : 1);     // stage-1 / stage-2 positions
       auto issue1 = [&](int i) {
-        const int xb = i % NX, db = i % ND;
-        mbar_wait(x_full(xb), (uint32_t)(i / NX) & 1u);
-        mbar_wait(d1_empty(db), ((uint32_t)(i / ND) & 1u) ^ 1u);
+        const int xb = x1.idx, db = d1.idx;
+        if (mt == 0) RP_TRACE(16, i);
+        mbar_wait(x_full(xb), x1.ph);
+        if (mt == 0) RP_TRACE(13, i);
+        mbar_wait(d1_empty(db), d1.ph ^ 1u);
         tc_fence_after();
+        if (mt == 0) RP_TRACE(1, i);
         const uint64_t da = make_smem_desc<BKC>(base + sp.x_off + xb * sp.xb + (uint32_t)(mt * 128) * RB);
-        run_conv(d1_col(db, mt), da, (uint64_t)((uint32_t)a.dil * RB >> 4), w1_res, a.stream1 != 0, 0u);
+        run_conv(d1_col(db, mt), da, (uint64_t)((uint32_t)a.dil * RB >> 4), x_chunk_step, w1_res, a.stream1 != 0, 0u);
         tc_commit(d1_full(db));
+        if (NT) tc_commit(x_empty(xb));      // stage 1 was the last tensor-pipe reader of the input tile
+        if (mt == 0) RP_TRACE(2, i);
+        x1.next(); d1.next();
       };
       auto issue2 = [&](int i) {
-        const int xb = i % NX, db = i % ND;
-        mbar_wait(t_full(xb), (uint32_t)(i / NX) & 1u);
-        mbar_wait(d2_init(db), (uint32_t)(i / ND) & 1u);
+        const int xb = x2.idx, db = d2.idx;
+        const int tb = NT ? t2.idx : xb;                       // stage-2 operand buffer
+        if (mt == 0) RP_TRACE(14, i);
+        mbar_wait(t_full(tb), NT ? t2.ph : x2.ph);
+        if (mt == 0) RP_TRACE(15, i);
+        mbar_wait(d2_init(db), d2.ph);
         tc_fence_after();
-        const uint64_t da = make_smem_desc<BKC>(base + sp.x_off + xb * sp.xb + (uint32_t)(mt * 128) * RB);
-        run_conv(d2_col(db, mt), da, (uint64_t)(RB >> 4), w2_res, a.stream2 != 0, 1u);
-        tc_commit(x_empty(xb));
+        if (mt == 0) RP_TRACE(3, i);
+        const uint32_t t_base = NT ? base + sp.t_off + tb * sp.tb : base + sp.x_off + xb * sp.xb;
+        const uint64_t da = make_smem_desc<BKC>(t_base + (uint32_t)(mt * 128) * RB);
+        run_conv(d2_col(db, mt), da, (uint64_t)(RB >> 4), NT ? t_chunk_step : x_chunk_step, w2_res, a.stream2 != 0, 1u);
+        tc_commit(NT ? t_empty(tb) : x_empty(xb));
         tc_commit(d2_full(db));
+        if (mt == 0) RP_TRACE(4, i);
+        x2.next(); d2.next(); t2.next();
       };
       if (a.pipelined) {
         // stage 1 of tile i+1 is issued before stage 2 of tile i: the tensor pipe works on it while
@@ -291,77 +356,116 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
     const int q = warp & 3;
     const int mt = (warp - 4) >> 2;      // this warp's M-tile
     const float slope = a.slope, inv_slope = a.inv_slope;
-    for (int i = 0; i < n_local; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int b = tile / a.tiles_per_item, tt = tile - b * a.tiles_per_item;
-      const int xb = i % NX, db = i % ND;
+    RingPos xr(NX), dr(ND), tr(NT ? NT : 1);
+    TilePos tp(blockIdx.x, gridDim.x, a.tiles_per_item);
+    for (int i = 0; i < n_local; ++i, xr.next(), dr.next(), tr.next(), tp.next()) {
+      const int b = tp.b, tt = tp.tt;
+      const int xb = xr.idx, db = dr.idx;
       const int o0 = tt * a.R_out;
       int len_b = a.L;
       if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
       const uint32_t xa = base + sp.x_off + xb * sp.xb;
-      mbar_wait(x_full(xb), (uint32_t)(i / NX) & 1u);
-      mbar_wait(d2_empty(db), ((uint32_t)(i / ND) & 1u) ^ 1u);
-      tc_fence_after();
-      {
-        const uint32_t arow = (uint32_t)(mt * 128 + q * 32 + lane + a.p1 + a.p2);
-        const uint32_t swz = (BKC == 64) ? (arow & 7u) : ((arow >> 1) & 3u);
-        const uint32_t rbase = xa + arow * RB;
-        const uint32_t tcol = d2_col(db, mt) + (uint32_t(q * 32) << 16);
+      const int tb = NT ? tr.idx : xb;
+      // seed: D2 <- residual (inverse LeakyReLU of the input tile's rows) + bias2
+      auto seed = [&]() {
+        mbar_wait(x_full(xb), xr.ph);
+        mbar_wait(d2_empty(db), dr.ph ^ 1u);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) RP_TRACE(5, i);
+        if (!(a.dbg & 16)) {
+          const uint32_t arow = (uint32_t)(mt * 128 + q * 32 + lane + a.p1 + a.p2);
+          const uint32_t swz = (BKC == 64) ? (arow & 7u) : ((arow >> 1) & 3u);
+          const uint32_t rbase = xa + arow * RB;
+          const uint32_t tcol = d2_col(db, mt) + (uint32_t(q * 32) << 16);
 #pragma unroll
-        for (int cc = 0; cc < C / 16; ++cc) {
-          const int c = (cc * 2) / UPC, u = (cc * 2) % UPC;
-          const uint4 t0 = lds128(rbase + c * chunk_bytes + (((uint32_t)u ^ swz) << 4));
-          const uint4 t1 = lds128(rbase + c * chunk_bytes + (((uint32_t)(u + 1) ^ swz) << 4));
-          const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-          uint32_t r[16];
+          for (int cc = 0; cc < C / 16; ++cc) {
+            const int c = (cc * 2) / UPC, u = (cc * 2) % UPC;
+            const uint4 t0 = lds128(rbase + c * chunk_bytes + (((uint32_t)u ^ swz) << 4));
+            const uint4 t1 = lds128(rbase + c * chunk_bytes + (((uint32_t)(u + 1) ^ swz) << 4));
+            const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            uint32_t r[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v0, v1;
-            unpack2<BF16>(w[e], v0, v1);
-            v0 = (v0 < 0.f ? v0 * inv_slope : v0) + bias_s[C + cc * 16 + 2 * e];
-            v1 = (v1 < 0.f ? v1 * inv_slope : v1) + bias_s[C + cc * 16 + 2 * e + 1];
-            r[2 * e] = __float_as_uint(v0); r[2 * e + 1] = __float_as_uint(v1);
+            for (int e = 0; e < 8; ++e) {
+              float v0, v1;
+              unpack2<BF16>(w[e], v0, v1);
+              // inverse LeakyReLU without a compare / select: inv_slope >= 1, so v * inv_slope <= v exactly when v <= 0
+              v0 = fminf(v0, v0 * inv_slope) + bias_s[C + cc * 16 + 2 * e];
+              v1 = fminf(v1, v1 * inv_slope) + bias_s[C + cc * 16 + 2 * e + 1];
+              r[2 * e] = __float_as_uint(v0); r[2 * e + 1] = __float_as_uint(v1);
+            }
+            tc_st16(tcol + (uint32_t)(cc * 16), r);
           }
-          tc_st16(tcol + (uint32_t)(cc * 16), r);
         }
-      }
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d2_init(db));
-
-      mbar_wait(d1_full(db), (uint32_t)(i / ND) & 1u);
-      tc_fence_after();
-      group_sync(1);   // every warp of the group has read its residual rows: the tile may be overwritten
-      {
-        const uint32_t m = (uint32_t)(mt * 128 + q * 32 + lane);
-        const int trow = o0 - a.p2 + (int)m;
-        const bool valid = trow >= 0 && trow < len_b;
-        const uint32_t swz = (BKC == 64) ? (m & 7u) : ((m >> 1) & 3u);
-        const uint32_t rbase = xa + m * RB;
-        const uint32_t tcol = d1_col(db, mt) + (uint32_t(q * 32) << 16);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(d2_init(db));
+          if (NT) mbar_arrive(x_empty(xb));      // this warp's residual rows are in TMEM
+        }
+        if (warp == 4 && lane == 0) RP_TRACE(6, i);
+      };
+      // epilogue 1: D1 -> + bias1 -> LeakyReLU -> zero outside the sequence -> 16-bit stage-2 operand
+      auto epi1 = [&]() {
+        mbar_wait(d1_full(db), dr.ph);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) RP_TRACE(7, i);
+        if (NT) mbar_wait(t_empty(tb), tr.ph ^ 1u);   // stage 2 of tile i - NT has read the buffer
+        else group_sync(1);   // every warp of the group has read its residual rows: the tile may be overwritten
+        if (warp == 4 && lane == 0) RP_TRACE(8, i);
+        const uint32_t t_cb = NT ? t_chunk_bytes : chunk_bytes;
+        if (!(a.dbg & 8)) {
+          const uint32_t m = (uint32_t)(mt * 128 + q * 32 + lane);
+          const int trow = o0 - a.p2 + (int)m;
+          const bool valid = trow >= 0 && trow < len_b;
+          const bool all_valid = !(a.dbg & 64) && __all_sync(0xffffffffu, valid);   // true for all but the tiles at a sequence's ends
+          const uint32_t swz = (BKC == 64) ? (m & 7u) : ((m >> 1) & 3u);
+          const uint32_t rbase = (NT ? base + sp.t_off + tb * sp.tb : xa) + m * RB;
+          const uint32_t tcol = d1_col(db, mt) + (uint32_t(q * 32) << 16);
 #pragma unroll
-        for (int cc = 0; cc < C / 16; ++cc) {
-          uint32_t r[16];
-          tc_ld16(tcol + (uint32_t)(cc * 16), r);
-          tc_wait_ld();
-          float v[16];
+          for (int c32 = 0; c32 < C / 32; ++c32) {
+            // one TMEM round trip per 32 columns (two loads in flight, one wait)
+            uint32_t r[2][16];
+            tc_ld16(tcol + (uint32_t)(c32 * 32), r[0]);
+            tc_ld16(tcol + (uint32_t)(c32 * 32 + 16), r[1]);
+            tc_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float t = __uint_as_float(r[e]) + bias_s[cc * 16 + e];
-            v[e] = valid ? fmaxf(t, t * slope) : 0.f;
+            for (int h = 0; h < 2; ++h) {
+              const int cc = c32 * 2 + h;
+              float v[16];
+#pragma unroll
+              if (all_valid) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float t = __uint_as_float(r[h][e]) + bias_s[cc * 16 + e];
+                  v[e] = fmaxf(t, t * slope);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float t = __uint_as_float(r[h][e]) + bias_s[cc * 16 + e];
+                  v[e] = valid ? fmaxf(t, t * slope) : 0.f;
+                }
+              }
+              const int c = (cc * 2) / UPC, u = (cc * 2) % UPC;
+              sts128(rbase + c * t_cb + (((uint32_t)u ^ swz) << 4),
+                     make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+              sts128(rbase + c * t_cb + (((uint32_t)(u + 1) ^ swz) << 4),
+                     make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+            }
           }
-          const int c = (cc * 2) / UPC, u = (cc * 2) % UPC;
-          sts128(rbase + c * chunk_bytes + (((uint32_t)u ^ swz) << 4),
-                 make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
-          sts128(rbase + c * chunk_bytes + (((uint32_t)(u + 1) ^ swz) << 4),
-                 make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
         }
-      }
-      tc_fence_before();
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(d1_empty(db)); mbar_arrive(t_full(xb)); }
+        if (warp == 4 && lane == 0) RP_TRACE(9, i);
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(d1_empty(db)); mbar_arrive(t_full(tb)); }
+        if (warp == 4 && lane == 0) RP_TRACE(10, i);
+      };
+      // With its own operand buffer, epilogue 1 of tile i depends only on stage 1 of tile i, while the seed has to
+      // wait for the drain of tile i - 2 (the D2 buffer): doing the epilogue first takes ~1000 cycles of this group's
+      // work out of the D2 buffer's seed -> stage 2 -> drain cycle.  In place, the seed must read the rows first.
+      if (NT) { epi1(); seed(); } else { seed(); epi1(); }
     }
   } else if (warp >= 12) {
     // ===== stage-2 group: epilogue 2 (D2 -> other branches, scale, mask, activation -> TMA store) =====
@@ -371,79 +475,110 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
     const uint32_t swz = (BKC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
     const float scale = a.out_scale, aslope = a.out_slope_eff;
     const bool has_res = a.res2 != nullptr || a.res3 != nullptr;
-    int nst = 0;
-    for (int i = 0; i < n_local; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int b = tile / a.tiles_per_item, tt = tile - b * a.tiles_per_item;
-      const int db = i % ND;
+    RingPos dr(ND), sr(a.NSTG);
+    TilePos tp(blockIdx.x, gridDim.x, a.tiles_per_item);
+    for (int i = 0; i < n_local; ++i, dr.next(), tp.next()) {
+      const int b = tp.b, tt = tp.tt;
+      const int db = dr.idx;
       const int o0 = tt * a.R_out;
       int len_b = a.L;
       if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
-      mbar_wait(d2_full(db), (uint32_t)(i / ND) & 1u);
+      mbar_wait(d2_full(db), dr.ph);
       tc_fence_after();
+      if (warp == 12 && lane == 0) RP_TRACE(11, i);
       {
         const int o = mt * 128 + q * 32 + lane;
         const int grow = o0 + o;
         const bool masked = grow >= len_b;
+        // most tiles: nothing masked, no scaling (only the last pair of a stage averages the MRF branches)
+        const bool plain = !(a.dbg & 64) && scale == 1.f && !__any_sync(0xffffffffu, masked);
         const int rows_here = min(32, a.R_out - (mt * 128 + q * 32));   // warp-uniform
         const uint32_t tcol = d2_col(db, mt) + (uint32_t(q * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < KCH; ++c) {
-          const uint32_t stg = stg0 + (uint32_t)(nst % a.NSTG) * 32u * RB;
-          ++nst;
+          const uint32_t stg = stg0 + (uint32_t)sr.idx * 32u * RB;
+          sr.next();
           if (lane == 0) { if (a.NSTG > 1) bulk_wait_read1(); else bulk_wait_read0(); }
           __syncwarp();
 #pragma unroll
-          for (int cc = 0; cc < BKC / 16; ++cc) {
-            const int c0 = c * BKC + cc * 16;
-            uint32_t r[16];
-            tc_ld16(tcol + (uint32_t)c0, r);
-            tc_wait_ld();
-            float v[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-            if (has_res && o < a.R_out && grow < a.L) {
+          for (int c32 = 0; c32 < BKC / 32; ++c32) {
+            // one TMEM round trip per 32 columns; the other MRF branches' rows are fetched while it is in flight
+            const int cb = c * BKC + c32 * 32;
+            uint32_t r[2][16];
+            tc_ld16(tcol + (uint32_t)cb, r[0]);
+            tc_ld16(tcol + (uint32_t)(cb + 16), r[1]);
+            uint4 g2[4], g3[4];
+            const bool add_res = has_res && o < a.R_out && grow < a.L;
+            if (add_res) {
               const long long rrow = (long long)b * a.L + grow;
               if (a.res2 != nullptr) {
-                const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res2) + rrow * a.res2_ld + c0);
-                const uint4 t0 = __ldg(p), t1 = __ldg(p + 1);
-                unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
-                unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
-                unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
-                unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+                const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res2) + rrow * a.res2_ld + cb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g2[j] = __ldg(p + j);
               }
               if (a.res3 != nullptr) {
-                const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res3) + rrow * a.res3_ld + c0);
-                const uint4 t0 = __ldg(p), t1 = __ldg(p + 1);
-                unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
-                unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
-                unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
-                unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+                const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res3) + rrow * a.res3_ld + cb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g3[j] = __ldg(p + j);
               }
             }
+            tc_wait_ld();
+            if (warp == 12 && lane == 0 && c == 0 && c32 == 0) RP_TRACE(17, i);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float t = masked ? 0.f : v[e] * scale;
-              v[e] = fmaxf(t, t * aslope);
+            for (int h = 0; h < 2; ++h) {
+              const int cc = c32 * 2 + h;
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[h][e]);
+              if (add_res) {
+                if (a.res2 != nullptr) {
+                  const uint4 t0 = g2[2 * h], t1 = g2[2 * h + 1];
+                  unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+                  unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+                  unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+                  unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+                }
+                if (a.res3 != nullptr) {
+                  const uint4 t0 = g3[2 * h], t1 = g3[2 * h + 1];
+                  unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+                  unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+                  unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+                  unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+                }
+              }
+              if (plain) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], v[e] * aslope);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float t = masked ? 0.f : v[e] * scale;
+                  v[e] = fmaxf(t, t * aslope);
+                }
+              }
+              const uint32_t o_lo = stg + (uint32_t)lane * RB + ((((uint32_t)(2 * cc)) ^ swz) << 4);
+              const uint32_t o_hi = stg + (uint32_t)lane * RB + ((((uint32_t)(2 * cc + 1)) ^ swz) << 4);
+              sts128(o_lo, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+              sts128(o_hi, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
             }
-            const uint32_t o_lo = stg + (uint32_t)lane * RB + ((((uint32_t)(2 * cc)) ^ swz) << 4);
-            const uint32_t o_hi = stg + (uint32_t)lane * RB + ((((uint32_t)(2 * cc + 1)) ^ swz) << 4);
-            sts128(o_lo, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
-            sts128(o_hi, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
           }
+          if (warp == 12 && lane == 0 && c == KCH - 1) RP_TRACE(18, i);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (rows_here >= 32) tma_store_3d(&maps.y, stg, c * BKC, o0 + mt * 128 + q * 32, b);
+            if (a.dbg & 2) {}
+            else if (rows_here >= 32) tma_store_3d(&maps.y, stg, c * BKC, o0 + mt * 128 + q * 32, b);
             else if (rows_here > 0) tma_store_3d(&maps.y_tail, stg, c * BKC, o0 + mt * 128 + q * 32, b);
             bulk_commit();
           }
           __syncwarp();
         }
       }
+      if (warp == 12 && lane == 0) RP_TRACE(19, i);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d2_empty(db));
+      if (warp == 12 && lane == 0) RP_TRACE(12, i);
     }
     if (lane == 0) bulk_wait_all0();
   }
@@ -474,6 +609,12 @@ static int env_int(const char* name, int dflt) {
 }
 
 }  // namespace asb
+
+// development aid, not part of the public header: copies the hand-off trace of the last ASB_PAIR_DBG=32 launch
+extern "C" int as_debug_pair_trace(unsigned long long* host, int n) {
+  if (n > 20 * 32) n = 20 * 32;
+  return asb::check_cuda(cudaMemcpyFromSymbol(host, asb::g_pair_trace, sizeof(unsigned long long) * n), "trace");
+}
 
 extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* stream) {
   using namespace asb;
@@ -513,43 +654,59 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   a.tiles_per_item = (p->L + a.R_out - 1) / a.R_out;
   a.total_tiles = p->B * a.tiles_per_item;
   a.ND = C <= 64 ? 2 : 1;
-  // shared-memory plan: weights resident when they fit next to two activation buffers, else conv1
-  // (then both) streamed through a ring; remaining room goes to a 2nd staging buffer, then more buffers
+  // shared-memory plan.  C <= 64: the stage-2 operand gets its own buffers (NT = 2, else 1), so an input buffer is
+  // held only from its TMA load to the end of stage 1 and the load of tile i + NX overlaps everything after that
+  // (measured: with the operand written in place the buffer lived for a whole tile, and the tensor pipe idled for
+  // the 2-4k cycles of every load).  Weights are resident when they fit next to that, otherwise conv1's (then both)
+  // stream from L2 through an mbarrier ring.  C = 128: one input buffer, operand in place, weights streamed.
+  // Remaining room goes to the weight ring, a second staging buffer, then more input buffers (up to 8).
   const size_t cap = 227 * 1024 - 1024;
   const size_t nblk = (size_t)k * KCH;
   int best_found = 0;
   const int mode_lo = env_int("ASB_PAIR_MODE", 0);
-  for (int mode = mode_lo; mode < 3 && !best_found; ++mode) {   // 0: resident, 1: conv1 streamed, 2: both streamed
-    a.stream1 = mode >= 1; a.stream2 = mode >= 2;
-    for (int nx = 2; nx >= 1 && !best_found; --nx) {
-      if (mode == 0 && nx == 1) continue;                 // prefer streaming conv1 over a single buffer
-      a.NX = nx; a.NSTG = 1;
-      a.SW = mode == 0 ? 0 : 3;
-      if (pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2).total > cap) continue;
-      best_found = 1;
-      if (mode > 0) {
-        const int want = (int)((a.stream1 ? nblk : 0) + (a.stream2 ? nblk : 0));
-        while (a.SW < 16 && a.SW < want && pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW + 1, a.stream1, a.stream2).total <= cap) ++a.SW;
+  const int nt_force = env_int("ASB_PAIR_NT", -1);
+  auto fits = [&](int nx, int nt, int nstg, int sw, int s1, int s2) {
+    return pair_smem(C, a.HA, k, nx, nt, nstg, sw, s1, s2).total <= cap;
+  };
+  for (int nt = (C <= 64 ? 2 : 0); nt >= 0 && !best_found; --nt) {
+    if (nt_force >= 0 && nt != nt_force) continue;
+    for (int mode = mode_lo; mode < 3 && !best_found; ++mode) {   // 0: resident, 1: conv1 streamed, 2: both streamed
+      a.stream1 = mode >= 1; a.stream2 = mode >= 2;
+      for (int nx = 2; nx >= 1 && !best_found; --nx) {
+        if (nx == 1 && (mode == 0 || nt > 0)) continue;   // prefer streaming / fewer operand buffers over one input buffer
+        a.NX = nx; a.NT = nt; a.NSTG = 1;
+        a.SW = mode == 0 ? 0 : 3;
+        if (!fits(a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2)) continue;
+        best_found = 1;
+        if (mode > 0) {
+          const int want = (int)((a.stream1 ? nblk : 0) + (a.stream2 ? nblk : 0));
+          const int sw_max = nt > 0 ? 8 : 16;
+          while (a.SW < sw_max && a.SW < want && fits(a.NX, a.NT, a.NSTG, a.SW + 1, a.stream1, a.stream2)) ++a.SW;
+        }
+        if (fits(a.NX, a.NT, 2, a.SW, a.stream1, a.stream2)) a.NSTG = 2;
+        const int nx_max = nt > 0 ? 6 : 3;
+        while (a.NX < nx_max && (mode <= 1 || nt > 0) && fits(a.NX + 1, a.NT, a.NSTG, a.SW, a.stream1, a.stream2)) ++a.NX;
       }
-      if (pair_smem(C, a.HA, k, a.NX, 2, a.SW, a.stream1, a.stream2).total <= cap) a.NSTG = 2;
-      while (a.NX < 3 && mode <= 1 && pair_smem(C, a.HA, k, a.NX + 1, a.NSTG, a.SW, a.stream1, a.stream2).total <= cap) ++a.NX;
     }
   }
   if (!best_found) {
-    a.stream1 = a.stream2 = 1; a.NX = 1; a.NSTG = 1; a.SW = 2;
-    ASB_REQUIRE(pair_smem(C, a.HA, k, 1, 1, 2, 1, 1).total <= cap, AS_ERR_SHAPE, "as_hifigan_resblock_pair: tile does not fit in shared memory");
+    a.stream1 = a.stream2 = 1; a.NX = 1; a.NT = 0; a.NSTG = 1; a.SW = 2;
+    ASB_REQUIRE(fits(1, 0, 1, 2, 1, 1), AS_ERR_SHAPE, "as_hifigan_resblock_pair: tile does not fit in shared memory");
   }
   // tuning overrides (tools/prof_pair.py)
   a.NX = env_int("ASB_PAIR_NX", a.NX); a.NSTG = env_int("ASB_PAIR_NSTG", a.NSTG); a.SW = env_int("ASB_PAIR_SW", a.SW);
-  // pipelined issue order needs two accumulator sets and two tiles in flight; with only conv1 streamed the
-  // ring is still consumed in tile order (stage 1 of tile 0, 1, 2, ...), with conv2 streamed it is not
-  a.pipelined = (a.ND == 2 && a.NX >= 2 && !a.stream2) ? 1 : 0;
+  // pipelined issue order (stage 1 of tile i + 1 before stage 2 of tile i) needs two accumulator sets and two tiles
+  // in flight; the weight ring is filled in the same order
+  a.pipelined = (a.ND == 2 && a.NX >= 2) ? 1 : 0;
   a.pipelined = env_int("ASB_PAIR_PIPE", a.pipelined);
-  if (a.stream2 || a.ND < 2 || a.NX < 2) a.pipelined = 0;
-  const PairSmem sp = pair_smem(C, a.HA, k, a.NX, a.NSTG, a.SW, a.stream1, a.stream2);
-  ASB_REQUIRE(sp.total <= cap && a.NX >= 1 && a.NX <= 4 && a.NSTG >= 1 && a.NSTG <= 2 && a.SW <= 16 &&
+  if (a.ND < 2 || a.NX < 2) a.pipelined = 0;
+  const PairSmem sp = pair_smem(C, a.HA, k, a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2);
+  ASB_REQUIRE(sp.total <= cap && a.NX >= 1 && a.NX <= 8 && a.NT >= 0 && a.NT <= 2 && a.NSTG >= 1 && a.NSTG <= 2 && a.SW <= 16 &&
                   (!(a.stream1 || a.stream2) || a.SW >= 2),
               AS_ERR_SHAPE, "as_hifigan_resblock_pair: invalid shared-memory plan (%u bytes)", sp.total);
+  if (env_int("ASB_PAIR_VERBOSE", 0))
+    fprintf(stderr, "pair C=%d k=%d dil=%d: NX=%d NT=%d ND=%d NSTG=%d SW=%d stream=%d%d pipelined=%d smem=%u\n", C, k, p->dil,
+            a.NX, a.NT, a.ND, a.NSTG, a.SW, a.stream1, a.stream2, a.pipelined, sp.total);
 
   const uint32_t fmt = (p->dtype == AS_BF16) ? 1u : 0u;
   a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(C >> 3) << 17) | (uint32_t(128 >> 4) << 24);
@@ -559,6 +716,7 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   a.out_scale = p->out_scale;
   a.out_slope_eff = p->out_act == AS_ACT_LRELU ? p->out_slope : 1.0f;
   a.lens = p->lens;
+  a.dbg = env_int("ASB_PAIR_DBG", 0);
 
   const CUtensorMapDataType dt = p->dtype == AS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = BKC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;

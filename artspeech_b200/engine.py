@@ -118,6 +118,15 @@ class Synthesizer:
                                               host_lengths=ml))
 
     # -- the two phases (models.ArtsSpeech.encode / decode + the vocoder) ---------------------------------------
+    @staticmethod
+    def _nvtx(name):
+        """NVTX range per phase (visible in nsys / ncu --nvtx timelines) when ASB_NVTX=1; also recorded at capture
+        time, so a captured graph's kernels carry the phase they belong to."""
+        import contextlib
+        if os.environ.get("ASB_NVTX") == "1":
+            return torch.cuda.nvtx.range(name)
+        return contextlib.nullcontext()
+
     def _sm_limit(self, n):
         if self.acoustic_sms and self.pipeline_depth > 1:
             _lib.load().as_set_sm_limit(n)
@@ -125,7 +134,8 @@ class Synthesizer:
     def _phase_a(self, tok, lens_t, mels, mel_lens_dev, host_mel_lens, voice, predict):
         self._sm_limit(self.acoustic_sms)
         try:
-            return self.model.encode(tok, lens_t, mels, mel_lens_dev, host_mel_lens, voice, predict)
+            with self._nvtx("asb.encode (text / arts / style encoders, duration predictor)"):
+                return self.model.encode(tok, lens_t, mels, mel_lens_dev, host_mel_lens, voice, predict)
         finally:
             self._sm_limit(0)
 
@@ -134,10 +144,12 @@ class Synthesizer:
         gen = self.generator
         try:
             self._sm_limit(self.acoustic_sms)
-            mel_cl, aux = self.model.decode(st, dur, Lmax, mel16_dtype=gen.compute_dtype)
+            with self._nvtx("asb.decode (length regulator, F0/N/EMA predictors, mel decoder)"):
+                mel_cl, aux = self.model.decode(st, dur, Lmax, mel16_dtype=gen.compute_dtype)
             self._sm_limit(max(2, total - self.acoustic_sms))
-            wav = gen.forward_channels_last(aux["mel16"], aux["mel_lengths"],
-                                            torch.int16 if self.pcm16 else torch.float32)
+            with self._nvtx("asb.vocoder (HiFi-GAN generator)"):
+                wav = gen.forward_channels_last(aux["mel16"], aux["mel_lengths"],
+                                                torch.int16 if self.pcm16 else torch.float32)
         finally:
             self._sm_limit(0)
         mel = ops.to_channels_first(mel_cl, torch.float32)

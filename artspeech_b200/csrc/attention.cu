@@ -427,6 +427,15 @@ conformer_attention_tiled_kernel(const float* __restrict__ q, const float* __res
 
 }  // namespace asb
 
+namespace asb {
+int relpos_attention_mma_launch(const float* qkv, long long ld, const float* relk, const float* relv, int window, int B,
+                                int T, int H, const int* lens, void* out, int odt, long long out_ld, cudaStream_t st);
+bool conformer_mma_eligible(int T);
+int conformer_attention_mma_launch(const float* q, const float* k, const float* v, long long ld, const float* pos,
+                                   const float* ub, const float* vb, int B, int T, int H, const int* lens, void* out,
+                                   int odt, long long out_ld, cudaStream_t st);
+}
+
 using namespace asb;
 
 extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float* emb_rel_k,
@@ -437,6 +446,13 @@ extern "C" int as_relpos_attention(const float* qkv, int64_t qkv_ld, const float
   ASB_REQUIRE(qkv && emb_rel_k && emb_rel_v && out, AS_ERR_SHAPE, "as_relpos_attention: null pointer");
   ASB_REQUIRE(D == 128, AS_ERR_SHAPE, "as_relpos_attention: head dim %d unsupported (128 only)", D);
   ASB_REQUIRE(window >= 0 && 2 * window + 1 <= RA_MAXW, AS_ERR_SHAPE, "as_relpos_attention: window");
+  // tensor-core path (mma.sync, fp16 operands / fp32 accumulate and softmax): 16-byte aligned rows, fp32 or
+  // 16-bit output; ASB_ATTN_FP32=1 keeps the all-fp32 CUDA-core kernel (numerics reference)
+  static const bool fp32_only = getenv("ASB_ATTN_FP32") != nullptr;
+  if (!fp32_only && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (qkv_ld % 4) == 0 && (out_ld % 2) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (reinterpret_cast<uintptr_t>(emb_rel_k) & 15) == 0)
+    return relpos_attention_mma_launch(qkv, qkv_ld, emb_rel_k, emb_rel_v, window, B, T, H, lens, out, out_dtype, out_ld,
+                                       reinterpret_cast<cudaStream_t>(stream));
   const int Tpad = (T + 31) & ~31;
   const size_t smem = sizeof(float) * ((size_t)RA_KT * (D + 4) + RA_QT * D + RA_QT * RA_MAXW + 2 * RA_MAXW * D + (size_t)RA_QT * Tpad);
   ASB_REQUIRE(smem <= 200 * 1024, AS_ERR_SHAPE, "as_relpos_attention: T=%d too long for the score buffer", T);
@@ -457,6 +473,15 @@ extern "C" int as_conformer_attention(const float* q, const float* k, const floa
   ASB_REQUIRE(q && k && v && pos && u_bias && v_bias && out, AS_ERR_SHAPE, "as_conformer_attention: null pointer");
   ASB_REQUIRE(D == 64, AS_ERR_SHAPE, "as_conformer_attention: head dim %d unsupported (64 only)", D);
   ASB_REQUIRE((qkv_ld % 4) == 0 && ((H * D) % 4) == 0, AS_ERR_ALIGN, "as_conformer_attention: ld must be a multiple of 4");
+  {
+    // tensor-core path (mma.sync, fp16 operands, fp32 accumulate / softmax); ASB_ATTN_FP32=1 keeps the fp32 kernels
+    static const bool fp32_only = getenv("ASB_ATTN_FP32") != nullptr;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!fp32_only && conformer_mma_eligible(T) && al16(q) && al16(k) && al16(v) && al16(pos) && al16(u_bias) && al16(v_bias) &&
+        (out_ld % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
+      return conformer_attention_mma_launch(q, k, v, qkv_ld, pos, u_bias, v_bias, B, T, H, lens, out, out_dtype, out_ld,
+                                            reinterpret_cast<cudaStream_t>(stream));
+  }
   const int Tpad = (T + 31) & ~31;
   {
     const size_t smem_t = sizeof(float) * ((size_t)(2 * CT_QT + 1) * D + 32 * (D + 4) + (size_t)(2 * CT_QT + 1) * Tpad);

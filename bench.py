@@ -520,6 +520,24 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     extras = {}
+    if rank == 0:
+        # host link probe: the e2e arm moves 15.4 MB of waveforms per step over PCIe; on a box whose link is slow or
+        # shared this copy, not the GPU, bounds e2e
+        hb = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        db = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        e0, e1 = _events()
+        link = {}
+        for name, (dst, src) in (("h2d_GBps", (db, hb)), ("d2h_GBps", (hb, db))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            link[name] = 4 * hb.numel() / (e0.elapsed_time(e1) / 1e3) / 1e9
+        extras["host_link"] = link
+        del hb, db
     if rank == 0 and world == 1:
         pk = peaks()
         e0, e1 = _events()

@@ -185,20 +185,37 @@ def test_embed_layernorm():
         _close(oa, ra, 1e-4)
 
 
-@pytest.mark.parametrize("T", [37, 150, 333])
-def test_relpos_attention(T):
+@pytest.mark.parametrize("out_dt", [torch.float32, torch.float16])
+@pytest.mark.parametrize("T", [37, 64, 150, 333, 928])
+def test_relpos_attention(T, out_dt):
+    """Tensor-core rel-pos attention (mma.sync, fp16 operands, fp32 accumulate / softmax) against the fp32 model of
+    RelTransformerEnc.py:138-169.  Tolerance = fp16 operand rounding (2^-11 relative on q, k, v and p): the end-to-end
+    mel tolerance of north_star is checked on top of it by tests/test_e2e_gpu.py."""
     torch.manual_seed(5)
     B, H, D = 2, 4, 128
     qkv = torch.randn(B, T, 3 * H * D)
     ek, ev = torch.randn(1, 9, D) * D ** -0.5, torch.randn(1, 9, D) * D ** -0.5
     lens = _lens(B, T)
     ref = sim.relpos_attention(qkv, ek, ev, 4, H, lens, torch.float32)
-    out = ops.relpos_attention(qkv.to(DEV), ek.to(DEV), ev.to(DEV), 4, H, lens.to(DEV), torch.float32)
-    _close(out, ref, 2e-5)
+    out = ops.relpos_attention(qkv.to(DEV), ek[0].contiguous().to(DEV), ev[0].contiguous().to(DEV), 4, H, lens.to(DEV), out_dt)
+    assert out.dtype == out_dt
+    _close(out, ref, 3e-3 if out_dt == torch.float32 else 4e-3)
+    for b in range(B):                         # rows beyond an utterance's length are exact zeros
+        assert float(out[b, int(lens[b]):].abs().max()) == 0.0 if int(lens[b]) < T else True
+    # a strided qkv view (row stride > 3*H*D) and peaked scores (large |q.k|: the online softmax must not overflow)
+    wide = torch.randn(B, T, 3 * H * D + 64)
+    wide[..., :H * D] *= 6.0
+    ref2 = sim.relpos_attention(wide[..., :3 * H * D].contiguous(), ek, ev, 4, H, lens, torch.float32)
+    out2 = ops.relpos_attention(wide.to(DEV)[..., :3 * H * D], ek[0].contiguous().to(DEV), ev[0].contiguous().to(DEV), 4, H,
+                                lens.to(DEV), out_dt)
+    assert bool(torch.isfinite(out2).all())
+    _close(out2, ref2, 2e-2)
 
 
-@pytest.mark.parametrize("T", [50, 240])
+@pytest.mark.parametrize("T", [50, 240, 431, 600])
 def test_conformer_attention(T):
+    """T <= 448: tensor-core kernel (mma.sync, fp16 operands, fp32 accumulate / softmax: tolerance = fp16 operand
+    rounding); longer sequences keep the fp32 CUDA-core kernel (position scores no longer fit in shared memory)."""
     torch.manual_seed(6)
     B, H, D = 2, 4, 64
     qkv = torch.randn(B, T, 3 * H * D)
@@ -210,7 +227,12 @@ def test_conformer_attention(T):
     g = qkv.to(DEV)
     out = ops.conformer_attention(g[..., :256], g[..., 256:512], g[..., 512:], pos.to(DEV), u.to(DEV), v.to(DEV),
                                   H, lens.to(DEV), torch.float32)
-    _close(out, ref, 2e-5)
+    _close(out, ref, 3e-3 if T <= 448 else 2e-5)
+    for b in range(B):
+        assert float(out[b, int(lens[b]):].abs().max()) == 0.0 if int(lens[b]) < T else True
+    out16 = ops.conformer_attention(g[..., :256], g[..., 256:512], g[..., 512:], pos.to(DEV), u.to(DEV), v.to(DEV),
+                                    H, lens.to(DEV), torch.float16)
+    _close(out16, ref, 4e-3)
 
 
 @pytest.mark.parametrize("up", [False, True])

@@ -264,10 +264,9 @@ bilstm128_mma_kernel(const float* __restrict__ xproj, long long xp_ld,
 // tile 0 = (i | f) x 8 units, tile 1 = (g | o) x 8 units, so i,f,g,o of a (unit, batch item) meet in
 // one thread and the cell update is register-only (fp32).  8 batch items per cluster.
 // ---------------------------------------------------------------------------------------------
-constexpr int L256_H = 256;
+// The same kernel can serve H = 128 with a cluster of 2 (64 units per CTA again); measured slower than the single-CTA
+// kernel above (see as_bilstm), so it is an experiment switch only.
 constexpr int L256_NB = 8;
-constexpr int L256_NC = 4;     // CTAs per cluster
-constexpr int L256_HP = 264;   // padded pitch (halves) of the h tile
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -286,12 +285,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int H, int L256_NC>
 __global__ void __cluster_dims__(L256_NC, 1, 1) __launch_bounds__(256, 1)
-bilstm256_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
-                         const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T,
-                         const int* __restrict__ lens, void* out, int odt, long long out_ld) {
+bilstm_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
+                      const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T,
+                      const int* __restrict__ lens, void* out, int odt, long long out_ld) {
   pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
-  constexpr int H = L256_H, G = 4 * H;
+  static_assert(H == 64 * L256_NC, "64 hidden units per CTA (8 warps x 8 units)");
+  constexpr int G = 4 * H;
+  constexpr int L256_HP = H + 8;   // padded pitch (halves) of the h tile
+  constexpr int KSTEPS = H / 16;
   __shared__ __align__(16) __half hs[2][L256_NB][L256_HP];
   __shared__ int s_len[L256_NB];
   const int dir = blockIdx.y;
@@ -313,12 +316,12 @@ bilstm256_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
   for (int i = 0; i < L256_NB; ++i) maxlen = max(maxlen, s_len[i]);
 
   // A fragments: tile tq rows 0..7 = gate 2tq, rows 8..15 = gate 2tq+1, both for units warp*8 + (row & 7)
-  uint32_t afrag[2][16][4];
+  uint32_t afrag[2][KSTEPS][4];
 #pragma unroll
   for (int tq = 0; tq < 2; ++tq) {
     const int r_lo = (2 * tq) * H + unit, r_hi = (2 * tq + 1) * H + unit;
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) {
+    for (int ks = 0; ks < KSTEPS; ++ks) {
       const int k0 = 16 * ks + 2 * tig;
       auto pk = [&](int r, int k) {
         __half2 v = __floats2half2_rn(Wt[(long long)k * G + r], Wt[(long long)(k + 1) * G + r]);
@@ -378,7 +381,7 @@ bilstm256_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
       acc[1][0] = xn[u][2][0]; acc[1][1] = xn[u][2][1]; acc[1][2] = xn[u][3][0]; acc[1][3] = xn[u][3][1];
       fetch(xn[u], s + PF);
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks) {
+      for (int ks = 0; ks < KSTEPS; ++ks) {
         const uint32_t bb0 = *reinterpret_cast<const uint32_t*>(hp + gid * L256_HP + 16 * ks + 2 * tig);
         const uint32_t bb1 = *reinterpret_cast<const uint32_t*>(hp + gid * L256_HP + 16 * ks + 2 * tig + 8);
         mma16816(acc[0], afrag[0][ks], bb0, bb1);
@@ -423,17 +426,26 @@ extern "C" int as_bilstm(const float* xproj, int64_t xproj_ld, const float* whh,
   ASB_REQUIRE(xproj && whh && out, AS_ERR_SHAPE, "as_bilstm: null pointer");
   ASB_REQUIRE(H == 128 || H == 256 || H == 64, AS_ERR_SHAPE, "as_bilstm: hidden size %d unsupported (64, 128 or 256)", H);
   if (H == 128) {
-    dim3 grid128((B + L128_NB - 1) / L128_NB, 2);
-    ASB_CUDA(launch_k(bilstm128_mma_kernel, grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
+    // the 2-CTA cluster split (64 units per CTA, h exchanged through DSMEM) halves the instructions per thread and step
+    // but was measured SLOWER (B200: 1.15 vs 1.02 us per step at B = 16, 1.59 vs 1.00 at 8 x 4800): the step is
+    // bound by its dependency chain (8 chained mma + MUFU chain + one barrier) and a cluster barrier costs more than
+    // __syncthreads.  ASB_LSTM128_CLUSTER=1 selects it for experiments.
+    static const bool cluster2 = getenv("ASB_LSTM128_CLUSTER") != nullptr;
+    if (!cluster2) {
+      dim3 grid128((B + L128_NB - 1) / L128_NB, 2);
+      ASB_CUDA(launch_k(bilstm128_mma_kernel, grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+          xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
+      return AS_OK;
+    }
+    dim3 grid(2 * ((B + L256_NB - 1) / L256_NB), 2);
+    ASB_CUDA(launch_k(bilstm_cluster_kernel<128, 2>, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream),
         xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
-    ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
   if (H == 256) {
-    dim3 grid256(L256_NC * ((B + L256_NB - 1) / L256_NB), 2);
-    ASB_CUDA(launch_k(bilstm256_cluster_kernel, grid256, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
+    dim3 grid256(4 * ((B + L256_NB - 1) / L256_NB), 2);
+    ASB_CUDA(launch_k(bilstm_cluster_kernel<256, 4>, grid256, 256, 0, reinterpret_cast<cudaStream_t>(stream),
         xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
-    ASB_CUDA(cudaGetLastError());
     return AS_OK;
   }
   const int G = 4 * H;

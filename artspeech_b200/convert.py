@@ -113,7 +113,7 @@ def install_cache(cache: dict, model, generator, device) -> None:
     want = {"acoustic": str(model.compute_dtype), "vocoder": str(generator.compute_dtype)}
     if cache["dtypes"] != want:
         raise ValueError(f"weight cache was packed for {cache['dtypes']}, the modules compute in {want}")
-    device = torch.device(device)
+    device = next(model.parameters()).device          # with its index ("cuda" -> "cuda:0"): what plan() compares with
     mods = {name: m for name, m in model.named_modules() if isinstance(m, nn_util.PlanMixin)}
     if set(mods) != set(cache["plans"]["acoustic"]):
         raise ValueError("weight cache does not match the module tree")

@@ -45,8 +45,11 @@ def timed(name, fn, reps=20):
 
 
 with torch.no_grad():
-    full = lambda: model([tok_d, tl_d, mel_d, ml_d], step="test", durations=dur_d, return_aux=True, host_meta=meta)
+    full = lambda: model([tok_d, tl_d, mel_d, ml_d], step="test", durations=dur_d, return_aux=True, host_meta=meta,
+                         predict_durations=True)
     mel, aux = timed("acoustic model (all)", full)
+    timed("durationPredictor", lambda: model.durationPredictor(tok_d, aux["ema_ext"], tl_d.to(torch.int32), ml_d,
+                                                                host_mel_lengths=meta["mel_lens"]))
     timed("text_encoder", lambda: model.text_encoder(tok_d, tl_d))
     timed("arts_encoder", lambda: model.arts_encoder(tok_d, tl_d))
     timed("style_encoder", lambda: model.style_encoder(mel_d, ml_d, "second", model.distribution, host_lengths=meta["mel_lens"]))

@@ -566,31 +566,35 @@ adain_tma_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbo
 // four elements.
 constexpr int ADR_THREADS = 512;    // 1024 threads (64 registers) measured slower: 23.5 vs 20.0 us at 16x800x1024
 constexpr int ADR_WARPS = ADR_THREADS / 32;
-constexpr int ADR_ROWS = ADR_WARPS * 4;   // rows covered per pass iteration
 constexpr int ADR_MAX_STAGES = 4;
 
 // MX: 0 <= slope <= 1, LeakyReLU(y) = max(y, slope * y) -- a template parameter so that the unrolled loops are branch-free
-template <bool UP, bool MX>
+template <bool UP, bool MX, int W>
 __global__ void __launch_bounds__(ADR_THREADS, 1)
 adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nbox, int C, int nslab, int units, int S,
                   const float* __restrict__ gb, long long gb_ld, float eps, float slope,
                   const int* __restrict__ lens, const float* __restrict__ up_w, const float* __restrict__ up_b,
                   void* out, int odt, long long out_ld, float* __restrict__ stats_out) {
   extern __shared__ __align__(128) float slab_raw[];
-  __shared__ __align__(16) float red[2][ADR_WARPS][32];     // per-warp partial sums / squared sums
-  __shared__ __align__(16) float tot[2][32];
+  // W = channels per slab (32, or 16 when that fills the SMs' last round better: see as_adain_norm_apply)
+  constexpr int CG = W / 4;                                 // 4-channel column groups per row
+  constexpr int RPW = 32 / CG;                              // rows a warp covers per pass
+  constexpr int ROWS = ADR_WARPS * RPW;                     // rows covered per pass iteration
+  constexpr uint32_t ROWB = 4u * W;                         // bytes per slab row
+  __shared__ __align__(16) float red[2][ADR_WARPS][W];      // per-warp partial sums / squared sums
+  __shared__ __align__(16) float tot[2][W];
   __shared__ __align__(8) unsigned long long bars[ADR_MAX_STAGES];
   float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(slab_raw) + 127) & ~uintptr_t(127));   // [S][nbox*BR][32]
-  const uint32_t slab_bytes = (uint32_t)nbox * BR * 128u;
+  const uint32_t slab_bytes = (uint32_t)nbox * BR * ROWB;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int r4 = lane >> 3, c4 = lane & 7;
-  const int row0 = w * 4 + r4;
+  const int r4 = lane / CG, c4 = lane % CG;
+  const int row0 = w * RPW + r4;
   auto issue = [&](int u, int stage) {                      // one thread: nbox bulk tensor copies, rows >= T / channels >= C arrive as zeros
     const uint32_t bar = smem_u32(&bars[stage]);
     const uint32_t dst = smem_u32(ring) + (uint32_t)stage * slab_bytes;
-    const int b = u / nslab, cb = (u - b * nslab) * 32;
+    const int b = u / nslab, cb = (u - b * nslab) * W;
     mbar_expect_tx(bar, slab_bytes);
-    for (int k = 0; k < nbox; ++k) tma_load_3d(dst + (uint32_t)k * BR * 128u, &tmx, bar, cb, k * BR, b);
+    for (int k = 0; k < nbox; ++k) tma_load_3d(dst + (uint32_t)k * BR * ROWB, &tmx, bar, cb, k * BR, b);
   };
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -610,7 +614,7 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
   // k for unit k + 1, consumed a whole unit later, so their L2 / DRAM latency never stalls the in-order pipeline
   // (ncu: with the loads next to their use, 30 % of the samples sat on the first instruction that reads gamma)
   auto load_scalars = [&](int u, int& len_o, float4& g_o, float4& be_o) {
-    const int b = u / nslab, c = (u - b * nslab) * 32 + 4 * c4;
+    const int b = u / nslab, c = (u - b * nslab) * W + 4 * c4;
     len_o = T;
     if (lens) { asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(len_o) : "l"(lens + b)); }
     if (c < C) {
@@ -623,7 +627,7 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
   float4 g_n = make_float4(0.f, 0.f, 0.f, 0.f), be_n = g_n;
   if ((int)blockIdx.x < units) load_scalars(blockIdx.x, len_n, g_n, be_n);
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int b = u / nslab, cb = (u - b * nslab) * 32, c = cb + 4 * c4;
+    const int b = u / nslab, cb = (u - b * nslab) * W, c = cb + 4 * c4;
     const bool cok = c < C;
     int len = len_n;
     const float4 g = g_n, be = be_n;
@@ -633,20 +637,20 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
     // explicit ld.shared: through the re-aligned generic pointer the compiler emits generic LD instead of LDS
     const uint32_t slab = smem_u32(ring) + (uint32_t)stage * slab_bytes + 16u * c4;
     auto row4 = [&](int t) -> float4 {
-      const uint4 r = lds128(slab + (uint32_t)t * 128u);
+      const uint4 r = lds128(slab + (uint32_t)t * ROWB);
       return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
     };
     const float4 pv = row4(0);
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
 #pragma unroll 4
-    for (int t = row0; t < len; t += ADR_ROWS) {
+    for (int t = row0; t < len; t += ROWS) {
       const float4 v = row4(t);
       const float dx = v.x - pv.x, dy = v.y - pv.y, dz = v.z - pv.z, dw = v.w - pv.w;
       s4.x += dx; s4.y += dy; s4.z += dz; s4.w += dw;
       q4.x = fmaf(dx, dx, q4.x); q4.y = fmaf(dy, dy, q4.y); q4.z = fmaf(dz, dz, q4.z); q4.w = fmaf(dw, dw, q4.w);
     }
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
+    for (int o = CG; o <= 16; o <<= 1) {
       s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
       s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
       q4.x += __shfl_xor_sync(0xffffffffu, q4.x, o); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, o);
@@ -657,8 +661,8 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
       *reinterpret_cast<float4*>(&red[1][w][4 * c4]) = q4;
     }
     __syncthreads();
-    if (threadIdx.x < 64) {                                 // 2 x 32 columns: one thread folds the 16 warps' partials
-      const int which = threadIdx.x >> 5, col = threadIdx.x & 31;
+    if (threadIdx.x < 2 * W) {                              // 2 x W columns: one thread folds the 16 warps' partials
+      const int which = threadIdx.x / W, col = threadIdx.x % W;
       float a = 0.f;
 #pragma unroll
       for (int i = 0; i < ADR_WARPS; ++i) a += red[which][i][col];
@@ -673,7 +677,7 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
       const float4 mean = make_float4(pv.x + md.x, pv.y + md.y, pv.z + md.z, pv.w + md.w);
       const float4 rstd = make_float4(rsqrtf(fmaxf(sq.x * inv_len - md.x * md.x, 0.f) + eps), rsqrtf(fmaxf(sq.y * inv_len - md.y * md.y, 0.f) + eps),
                                       rsqrtf(fmaxf(sq.z * inv_len - md.z * md.z, 0.f) + eps), rsqrtf(fmaxf(sq.w * inv_len - md.w * md.w, 0.f) + eps));
-      if (stats_out != nullptr && threadIdx.x < 8) {
+      if (stats_out != nullptr && threadIdx.x < CG) {
         float* so = stats_out + ((long long)b * C + c) * 2;
         so[0] = mean.x; so[1] = rstd.x; so[2] = mean.y; so[3] = rstd.y; so[4] = mean.z; so[5] = rstd.z; so[6] = mean.w; so[7] = rstd.w;
       }
@@ -696,26 +700,26 @@ adain_ring_kernel(const __grid_constant__ CUtensorMap tmx, int T, int BR, int nb
         if (odt != AS_F32) {
           // 16-bit output: 8 bytes per thread, 64 contiguous bytes per row; frames past the length are zeros
           uint2* o2 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + ((long long)b * T + row0) * out_ld + c);
-          const long long ostep = (long long)ADR_ROWS * out_ld / 4;     // in uint2 units (out_ld % 4 == 0)
+          const long long ostep = (long long)ROWS * out_ld / 4;     // in uint2 units (out_ld % 4 == 0)
           int t = row0;
           if (odt == AS_F16) {
 #pragma unroll 4
-            for (; t < len; t += ADR_ROWS, o2 += ostep) { const float4 v = act_row(t); *o2 = make_uint2(pack16(v.x, v.y, AS_F16), pack16(v.z, v.w, AS_F16)); }
+            for (; t < len; t += ROWS, o2 += ostep) { const float4 v = act_row(t); *o2 = make_uint2(pack16(v.x, v.y, AS_F16), pack16(v.z, v.w, AS_F16)); }
           } else {
 #pragma unroll 4
-            for (; t < len; t += ADR_ROWS, o2 += ostep) { const float4 v = act_row(t); *o2 = make_uint2(pack16(v.x, v.y, AS_BF16), pack16(v.z, v.w, AS_BF16)); }
+            for (; t < len; t += ROWS, o2 += ostep) { const float4 v = act_row(t); *o2 = make_uint2(pack16(v.x, v.y, AS_BF16), pack16(v.z, v.w, AS_BF16)); }
           }
-          for (; t < T; t += ADR_ROWS, o2 += ostep) *o2 = make_uint2(0u, 0u);
+          for (; t < T; t += ROWS, o2 += ostep) *o2 = make_uint2(0u, 0u);
         } else {
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-          for (int t = row0; t < T; t += ADR_ROWS) st4any(out, ((long long)b * T + t) * out_ld + c, t < len ? act_row(t) : z4, odt);
+          for (int t = row0; t < T; t += ROWS) st4any(out, ((long long)b * T + t) * out_ld + c, t < len ? act_row(t) : z4, odt);
         }
       } else {
         float w0[4], w1[4], w2[4], ub[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { w0[e] = up_w[(c + e) * 3]; w1[e] = up_w[(c + e) * 3 + 1]; w2[e] = up_w[(c + e) * 3 + 2]; ub[e] = up_b[c + e]; }
-        for (int t = row0; t < T; t += ADR_ROWS) {
+        for (int t = row0; t < T; t += ROWS) {
           float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), od = ev;
           if (t < len) {
             const float4 a0 = act_row(t), a1 = t + 1 < len ? act_row(t + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1451,30 +1455,40 @@ extern "C" int as_adain_norm_apply(const void* x, int32_t x_dtype, int64_t x_ld,
     EncodeTiledFn enc = get_encode_fn();
     static const bool no_ring = getenv("ASB_ADAIN_NO_RING") != nullptr;
     if (enc && !no_ring) {
-      // ring of S slabs [nbox * BR][32] fp32 in one persistent CTA per SM (see adain_ring_kernel)
+      // ring of S slabs [nbox * BR][W] fp32 in one persistent CTA per SM (see adain_ring_kernel).  Slab width: 32
+      // channels (128-byte rows); 16 channels when a 32-wide slab is too long for a two-stage ring (T > ~860), which
+      // takes sequences up to ~1700 frames from 2.8 to 4.0 TB/s.  (Measured and rejected: 16-wide slabs to fill the
+      // last round of the static unit schedule better -- 16 x 1024 channels are 3.46 units per SM with W = 32 and 6.92
+      // with W = 16 -- the 64-byte rows cost more than the tail: 22.4 vs 17.7 us at 16 x 800 x 1024.)
       const int nbox = (T + 255) / 256;
       const int BR = ((T + nbox - 1) / nbox + 7) / 8 * 8;
-      const size_t slab_bytes = (size_t)nbox * BR * 128;
+      const int nsm = num_sms();
+      static const int force_w = getenv("ASB_ADAIN_SLAB") ? atoi(getenv("ASB_ADAIN_SLAB")) : 0;
+      const bool two_stages_32 = (size_t)(216 * 1024) / ((size_t)nbox * BR * 128) >= 2;
+      const int W = force_w ? force_w : ((!two_stages_32 && (C % 16) == 0) ? 16 : 32);
+      const size_t slab_bytes = (size_t)nbox * BR * 4 * W;
       const int S = (int)std::min<size_t>(ADR_MAX_STAGES, (size_t)(216 * 1024) / slab_bytes);
       CUtensorMap tmx;
       cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
       cuuint64_t strides[2] = {(cuuint64_t)x_ld * 4, (cuuint64_t)x_ld * 4 * T};
-      cuuint32_t box[3] = {32, (cuuint32_t)BR, 1};
+      cuuint32_t box[3] = {(cuuint32_t)W, (cuuint32_t)BR, 1};
       cuuint32_t es3[3] = {1, 1, 1};
       if (S >= 2 && enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-        const int nslab = cdiv(C, 32), units = nslab * B;
+        const int nslab = cdiv(C, W), units = nslab * B;
         const size_t rsmem = (size_t)S * slab_bytes + 128;
-        dim3 rgrid((unsigned)std::min(units, num_sms()));
+        dim3 rgrid((unsigned)std::min(units, nsm));
         const bool mx = slope >= 0.f && slope <= 1.f;
-#define ADR_LAUNCH(UP_, MX_)                                                                                                    \
+#define ADR_LAUNCH(UP_, MX_, W_)                                                                                                \
   do {                                                                                                                          \
-    ASB_SMEM_OPT_IN(217 * 1024, adain_ring_kernel<UP_, MX_>);                                                                   \
-    ASB_CUDA(launch_k(adain_ring_kernel<UP_, MX_>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld, \
+    ASB_SMEM_OPT_IN(217 * 1024, adain_ring_kernel<UP_, MX_, W_>);                                                               \
+    ASB_CUDA(launch_k(adain_ring_kernel<UP_, MX_, W_>, rgrid, ADR_THREADS, rsmem, ST(stream), tmx, T, BR, nbox, C, nslab, units, S, gb, gb_ld, \
                       eps, slope, lens, up_w, up_b, out, out_dtype, out_ld, stats));                                            \
   } while (0)
-        if (up_w) { if (mx) ADR_LAUNCH(true, true); else ADR_LAUNCH(true, false); }
-        else { if (mx) ADR_LAUNCH(false, true); else ADR_LAUNCH(false, false); }
+#define ADR_LAUNCH_W(UP_, MX_) do { if (W == 16) ADR_LAUNCH(UP_, MX_, 16); else ADR_LAUNCH(UP_, MX_, 32); } while (0)
+        if (up_w) { if (mx) ADR_LAUNCH_W(true, true); else ADR_LAUNCH_W(true, false); }
+        else { if (mx) ADR_LAUNCH_W(false, true); else ADR_LAUNCH_W(false, false); }
+#undef ADR_LAUNCH_W
 #undef ADR_LAUNCH
         ASB_CUDA(cudaGetLastError());
         return AS_OK;

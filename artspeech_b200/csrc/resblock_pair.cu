@@ -47,6 +47,7 @@ struct PairArgs {
   int B, L, tiles_per_item, total_tiles;
   int k, dil, p1, p2, R_out, HA, HB, tail_rows;
   int NX, ND, NSTG, SW, stream1, stream2, pipelined;
+  int pair;  // 1: cluster of two CTAs, tcgen05.mma.cta_group::2 (each CTA holds half of every weight block)
   int NT;    // stage-2 operand buffers: 0 = written in place over the input tile, 1..2 = separate buffers (the
              // input tile is then released as soon as stage 1 and the residual read are done)
   int dbg;   // timing experiments only (ASB_PAIR_DBG; results are wrong): 1 no MMAs, 2 no stores, 4 no reloads, 8 no epilogue-1 math, 16 no seed
@@ -104,8 +105,8 @@ struct PairSmem {
   uint32_t xb, x_off, tb, t_off, wres_off, ring_off, stg_off, bias_off, bar_off, total;
 };
 constexpr uint32_t RP_NBARS = 96;
-__host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int NT, int NSTG, int SW, int stream1, int stream2) {
-  const uint32_t BKC = C >= 64 ? 64 : 32, RB = BKC * 2, KCH = C / BKC, WBLK = (uint32_t)C * RB;
+__host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int NT, int NSTG, int SW, int stream1, int stream2, int pair = 0) {
+  const uint32_t BKC = C >= 64 ? 64 : 32, RB = BKC * 2, KCH = C / BKC, WBLK = (uint32_t)(pair ? C / 2 : C) * RB;
   PairSmem s;
   s.xb = ((KCH * (uint32_t)HA * RB) + 1023u) & ~1023u;
   s.x_off = 0;
@@ -121,20 +122,29 @@ __host__ __device__ inline PairSmem pair_smem(int C, int HA, int k, int NX, int 
   return s;
 }
 
-template <int C, bool BF16>
-__global__ void __launch_bounds__(RP_THREADS, 1)
-resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairArgs a) {
+// PAIR: the kernel runs as clusters of two CTAs (one TPC).  Each CTA keeps its own tiles, buffers and epilogue groups;
+// the LEADER's two issuer warps drive both tensor cores with tcgen05.mma.cta_group::2 (UMMA M = 256: M-tile mt of both
+// CTAs in one instruction), and every weight block is split between the two CTAs' shared memories (C / 2 rows each),
+// so the operand bytes a CTA fetches per instruction drop from A + W to A + W / 2 (the pair kernels' MMA phases run at
+// the shared-memory operand limit).  Barrier topology: barriers the issuers WAIT on (x_full, d1_empty,
+// t_full, d2_init, weight-full) live in the leader and collect both CTAs' arrivals (TMA completions with
+// .cta_group::2, remote mbarrier arrives); barriers the issuers SIGNAL (d1_full, d2_full, x_empty, t_empty,
+// weight-empty) exist in both CTAs and are hit by one multicast tcgen05.commit.  x_full is relayed to both CTAs'
+// epilogue groups by a spare thread of the leader (x_seen).
+template <int C, bool BF16, bool PAIR>
+__device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const PairArgs& a) {
   constexpr int BKC = C >= 64 ? 64 : 32;       // channels per K chunk (one swizzled row)
   constexpr uint32_t RB = BKC * 2;             // bytes per row of a chunk
   constexpr int KCH = C / BKC;
-  constexpr uint32_t WBLK = (uint32_t)C * RB;  // one (tap, chunk) weight block
+  constexpr int WROWS = PAIR ? C / 2 : C;      // weight rows (output channels) this CTA holds of every block
+  constexpr uint32_t WBLK = (uint32_t)WROWS * RB;  // one (tap, chunk) weight block (this CTA's share)
   constexpr int KS = BKC / 16;                 // MMAs (K = 16) per chunk
   constexpr int UPC = BKC / 8;                 // 16-byte units per chunk row
   constexpr uint32_t TMEM_COLS = 512;
 
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const PairSmem sp = pair_smem(C, a.HA, a.k, a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2);
+  const PairSmem sp = pair_smem(C, a.HA, a.k, a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2, a.pair);
   const int NX = a.NX, ND = a.ND, SW = a.SW, NT = a.NT;
   const uint32_t t_chunk_bytes = 256u * RB;
   const uint32_t chunk_bytes = (uint32_t)a.HA * RB;
@@ -145,6 +155,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   auto x_empty = [&](int i) { return bars + 8u * (72 + i); };    // [8]
   auto t_full = [&](int i) { return bars + 8u * (8 + i); };      // [4]
   auto t_empty = [&](int i) { return bars + 8u * (80 + i); };    // [4]
+  auto x_seen = [&](int i) { return bars + 8u * (84 + i); };     // [8] pair mode: "input tile i landed in both CTAs"
   auto d1_full = [&](int i) { return bars + 8u * (12 + i); };    // [2]
   auto d1_empty = [&](int i) { return bars + 8u * (14 + i); };   // [2]
   auto d2_init = [&](int i) { return bars + 8u * (16 + i); };    // [2]
@@ -156,14 +167,38 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   const uint32_t tmem_slot = bars + 8u * 56;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // tile walk: a CTA (1-CTA mode) or a cluster (pair mode: the two CTAs take adjacent tiles) per schedule slot
+  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tiles_per_slot = PAIR ? 2 : 1;
+  const int first_tile = sched_id * tiles_per_slot + (int)rank;
+  const int tile_step = sched_n * tiles_per_slot;
+  const int n_slots = (a.total_tiles + tiles_per_slot - 1) / tiles_per_slot;
+  // barriers in the leader (as shared::cluster addresses when this is the peer)
+  auto on_leader = [&](uint32_t bar) { return (PAIR && !leader) ? mapa_u32(bar, 0) : bar; };
+  auto arrive_leader = [&](uint32_t bar) {
+    if (PAIR) mbar_arrive_cluster(mapa_u32(bar, 0));
+    else mbar_arrive(bar);
+  };
+  auto arrive_leader_relaxed = [&](uint32_t bar) {     // TMEM-only hand-offs (no memory writes to publish)
+    if (PAIR) mbar_arrive_cluster_relaxed(mapa_u32(bar, 0));
+    else mbar_arrive(bar);
+  };
+  auto commit = [&](uint32_t bar) {
+    if (PAIR) tc2_commit(bar);
+    else tc_commit(bar);
+  };
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bias_s[i] = i < C ? a.b1[i] : a.b2[i - C];
 
   if (threadIdx.x == 0) {
     // separate stage-2 buffers: the input tile is released by the two stage-1 commits + the eight residual readers
-    for (int i = 0; i < 8; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), a.NT ? 10 : 2); }
-    for (int i = 0; i < 4; ++i) { mbar_init(t_full(i), 8); mbar_init(t_empty(i), 2); }
+    const uint32_t ng = PAIR ? 16u : 8u;   // epilogue-group warps that arrive on a leader barrier (both CTAs' in pair mode)
+    for (int i = 0; i < 8; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), a.NT ? 10 : 2); mbar_init(x_seen(i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(t_full(i), ng); mbar_init(t_empty(i), 2); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full(i), 2); mbar_init(d1_empty(i), 8); mbar_init(d2_init(i), 8);
+      mbar_init(d1_full(i), 2); mbar_init(d1_empty(i), ng); mbar_init(d2_init(i), ng);
       mbar_init(d2_full(i), 2); mbar_init(d2_empty(i), 8);
     }
     mbar_init(wres_full, 1);
@@ -179,12 +214,17 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w2) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync();     // both CTAs' barriers are initialised and their TMEM is allocated (also a CTA barrier)
+  else __syncthreads();
   tc_fence_after();
   pdl_wait();   // barrier init / TMEM alloc / descriptor prefetch above overlap the previous kernel's tail
   uint32_t tmem_base;
@@ -193,31 +233,44 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   auto d1_col = [&](int buf, int mt) { return tmem_base + (uint32_t)((buf * 2 + mt) * C); };
   auto d2_col = [&](int buf, int mt) { return tmem_base + (uint32_t)((2 * ND + buf * 2 + mt) * C); };
 
-  const int n_local = ((int)blockIdx.x < a.total_tiles) ? (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_local = (sched_id < n_slots) ? (n_slots - sched_id + sched_n - 1) / sched_n : 0;   // same in both CTAs of a pair
   const int nblk = a.k * KCH;                                     // weight blocks per conv
   const uint32_t w1_res = base + sp.wres_off;                     // resident conv1 blocks (if !stream1)
   const uint32_t w2_res = base + sp.wres_off + (a.stream1 ? 0u : (uint32_t)nblk * WBLK);
   const uint32_t ring = base + sp.ring_off;
 
   if (warp == 0) {
+    if (PAIR && leader && lane == 1) {
+      // ===== relay (pair mode): x_full lives in the leader only; tell both CTAs' epilogue groups that tile i landed.
+      // A thread of its own because the cluster-scope release of the remote arrive stalls its issuer for ~1300 cycles.
+      RingPos xr(NX);
+      for (int i = 0; i < n_local; ++i, xr.next()) {
+        mbar_wait(x_full(xr.idx), xr.ph);
+        mbar_arrive(x_seen(xr.idx));
+        mbar_arrive_cluster(mapa_u32(x_seen(xr.idx), 1));
+      }
+    }
     if (lane == 0) {
       // ===== activation-tile producer =====
       RingPos xr(NX);
-      TilePos tp(blockIdx.x, gridDim.x, a.tiles_per_item);
+      TilePos tp(first_tile, tile_step, a.tiles_per_item);
       for (int i = 0; i < n_local; ++i, xr.next(), tp.next()) {
         const int b = tp.b, tt = tp.tt;
         const int xb = xr.idx;
         const uint32_t ph = xr.ph;
         mbar_wait(x_empty(xb), ph ^ 1u);
         RP_TRACE(0, i);
-        if ((a.dbg & 4) && i >= NX) { mbar_arrive(x_full(xb)); continue; }
-        mbar_expect_tx(x_full(xb), (uint32_t)KCH * chunk_bytes);
+        if ((a.dbg & 4) && i >= NX) { if (leader) mbar_arrive(x_full(xb)); continue; }
+        // pair mode: both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
+        if (leader) mbar_expect_tx(x_full(xb), (uint32_t)(PAIR ? 2 : 1) * KCH * chunk_bytes);
+        const uint32_t xfb = on_leader(x_full(xb));
         const int row0 = tt * a.R_out - a.p2 - a.p1;
         const uint32_t dst = base + sp.x_off + xb * sp.xb;
 #pragma unroll
         for (int c = 0; c < KCH; ++c)
           for (int h = 0; h < 2; ++h)
-            tma_load_3d(dst + c * chunk_bytes + h * a.HB * RB, &maps.x, x_full(xb), c * BKC, row0 + h * a.HB, b);
+            if (PAIR) tma2_load_3d(dst + c * chunk_bytes + h * a.HB * RB, &maps.x, xfb, c * BKC, row0 + h * a.HB, b);
+            else tma_load_3d(dst + c * chunk_bytes + h * a.HB * RB, &maps.x, xfb, c * BKC, row0 + h * a.HB, b);
       }
     }
   } else if (warp == 2) {
@@ -225,13 +278,16 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
       // ===== weight producer: resident blocks once, streamed blocks through the ring every tile =====
       const int nres = (a.stream1 ? 0 : nblk) + (a.stream2 ? 0 : nblk);
       if (nres > 0) {
-        mbar_expect_tx(wres_full, (uint32_t)nres * WBLK);
+        if (leader) mbar_expect_tx(wres_full, (uint32_t)(PAIR ? 2 : 1) * nres * WBLK);
+        const uint32_t wfb = on_leader(wres_full);
+        auto wload = [&](uint32_t dst, const CUtensorMap* wm, uint32_t bar, int j) {   // this CTA's rows of block j
+          if (PAIR) tma2_load_2d(dst, wm, bar, (j % KCH) * BKC, (j / KCH) * C + (int)rank * WROWS);
+          else tma_load_2d(dst, wm, bar, (j % KCH) * BKC, (j / KCH) * C);
+        };
         if (!a.stream1)
-          for (int j = 0; j < nblk; ++j)
-            tma_load_2d(w1_res + j * WBLK, &maps.w1, wres_full, (j % KCH) * BKC, (j / KCH) * C);
+          for (int j = 0; j < nblk; ++j) wload(w1_res + j * WBLK, &maps.w1, wfb, j);
         if (!a.stream2)
-          for (int j = 0; j < nblk; ++j)
-            tma_load_2d(w2_res + j * WBLK, &maps.w2, wres_full, (j % KCH) * BKC, (j / KCH) * C);
+          for (int j = 0; j < nblk; ++j) wload(w2_res + j * WBLK, &maps.w2, wfb, j);
       }
       if (a.stream1 || a.stream2) {
         // the ring is filled in the order the MMA issuers consume it: stage 1 and stage 2 of every tile, and in
@@ -244,8 +300,9 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
             const int slot = wr.idx;
             const uint32_t ph = wr.ph;
             mbar_wait(wr_empty(slot), ph ^ 1u);
-            mbar_expect_tx(wr_full(slot), WBLK);
-            tma_load_2d(ring + slot * WBLK, wm, wr_full(slot), (j % KCH) * BKC, (j / KCH) * C);
+            if (leader) mbar_expect_tx(wr_full(slot), (uint32_t)(PAIR ? 2 : 1) * WBLK);
+            if (PAIR) tma2_load_2d(ring + slot * WBLK, wm, on_leader(wr_full(slot)), (j % KCH) * BKC, (j / KCH) * C + (int)rank * WROWS);
+            else tma_load_2d(ring + slot * WBLK, wm, wr_full(slot), (j % KCH) * BKC, (j / KCH) * C);
           }
         };
         if (a.pipelined) {
@@ -265,7 +322,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
     // pipe busy (measured ~100 clk per instruction with a single issuer), so the issue stream is split
     // and kept branch-free: the warp stays converged, one elected lane issues. =====
     const int mt = warp == 1 ? 0 : 1;
-    if (elect_one()) {
+    if (leader && elect_one()) {
       if (!a.stream1 || !a.stream2) mbar_wait(wres_full, 0);
       int slot = 0;            // weight ring position (streamed convolutions, in-order mode only)
       uint32_t slot_ph = 0;
@@ -282,7 +339,8 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
             for (int c = 0; c < KCH; ++c, dw += (uint64_t)(WBLK >> 4)) {
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
-                if (do_mma) tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                if (do_mma) { if (PAIR) tc2_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                             else tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc); }
                 acc = 1u;
               }
             }
@@ -296,10 +354,11 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
               const uint64_t dw = make_smem_desc<BKC>(ring + slot * WBLK);
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
-                if (do_mma) tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                if (do_mma) { if (PAIR) tc2_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc);
+                             else tc_mma_f16(tacc, da_tap + (uint64_t)c * chunk_step + uint64_t(2 * ks), dw + uint64_t(2 * ks), idesc, acc); }
                 acc = 1u;
               }
-              tc_commit(wr_empty(slot));
+              commit(wr_empty(slot));
               if (++slot == SW) { slot = 0; slot_ph ^= 1u; }
             }
           }
@@ -316,8 +375,8 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
         if (mt == 0) RP_TRACE(1, i);
         const uint64_t da = make_smem_desc<BKC>(base + sp.x_off + xb * sp.xb + (uint32_t)(mt * 128) * RB);
         run_conv(d1_col(db, mt), da, (uint64_t)((uint32_t)a.dil * RB >> 4), x_chunk_step, w1_res, a.stream1 != 0, 0u);
-        tc_commit(d1_full(db));
-        if (NT) tc_commit(x_empty(xb));      // stage 1 was the last tensor-pipe reader of the input tile
+        commit(d1_full(db));
+        if (NT) commit(x_empty(xb));      // stage 1 was the last tensor-pipe reader of the input tile
         if (mt == 0) RP_TRACE(2, i);
         x1.next(); d1.next();
       };
@@ -333,8 +392,8 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
         const uint32_t t_base = NT ? base + sp.t_off + tb * sp.tb : base + sp.x_off + xb * sp.xb;
         const uint64_t da = make_smem_desc<BKC>(t_base + (uint32_t)(mt * 128) * RB);
         run_conv(d2_col(db, mt), da, (uint64_t)(RB >> 4), NT ? t_chunk_step : x_chunk_step, w2_res, a.stream2 != 0, 1u);
-        tc_commit(NT ? t_empty(tb) : x_empty(xb));
-        tc_commit(d2_full(db));
+        commit(NT ? t_empty(tb) : x_empty(xb));
+        commit(d2_full(db));
         if (mt == 0) RP_TRACE(4, i);
         x2.next(); d2.next(); t2.next();
       };
@@ -357,18 +416,19 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
     const int mt = (warp - 4) >> 2;      // this warp's M-tile
     const float slope = a.slope, inv_slope = a.inv_slope;
     RingPos xr(NX), dr(ND), tr(NT ? NT : 1);
-    TilePos tp(blockIdx.x, gridDim.x, a.tiles_per_item);
+    TilePos tp(first_tile, tile_step, a.tiles_per_item);
     for (int i = 0; i < n_local; ++i, xr.next(), dr.next(), tr.next(), tp.next()) {
       const int b = tp.b, tt = tp.tt;
       const int xb = xr.idx, db = dr.idx;
       const int o0 = tt * a.R_out;
       int len_b = a.L;
-      if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
+      if (b >= a.B) len_b = 0;                                   // the padding tile of an odd pair
+      else if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
       const uint32_t xa = base + sp.x_off + xb * sp.xb;
       const int tb = NT ? tr.idx : xb;
       // seed: D2 <- residual (inverse LeakyReLU of the input tile's rows) + bias2
       auto seed = [&]() {
-        mbar_wait(x_full(xb), xr.ph);
+        mbar_wait(PAIR ? x_seen(xb) : x_full(xb), xr.ph);
         mbar_wait(d2_empty(db), dr.ph ^ 1u);
         tc_fence_after();
         if (warp == 4 && lane == 0) RP_TRACE(5, i);
@@ -400,7 +460,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(d2_init(db));
+          arrive_leader_relaxed(d2_init(db));
           if (NT) mbar_arrive(x_empty(xb));      // this warp's residual rows are in TMEM
         }
         if (warp == 4 && lane == 0) RP_TRACE(6, i);
@@ -459,13 +519,15 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(d1_empty(db)); mbar_arrive(t_full(tb)); }
+        if (lane == 0) { arrive_leader_relaxed(d1_empty(db)); arrive_leader(t_full(tb)); }
         if (warp == 4 && lane == 0) RP_TRACE(10, i);
       };
       // With its own operand buffer, epilogue 1 of tile i depends only on stage 1 of tile i, while the seed has to
       // wait for the drain of tile i - 2 (the D2 buffer): doing the epilogue first takes ~1000 cycles of this group's
       // work out of the D2 buffer's seed -> stage 2 -> drain cycle.  In place, the seed must read the rows first.
-      if (NT) { epi1(); seed(); } else { seed(); epi1(); }
+      // With a single accumulator set (C = 128) the D2 buffer is free long before stage 1 ends: seed first, under
+      // stage 1's MMAs.
+      if (NT && ND == 2) { epi1(); seed(); } else { seed(); epi1(); }
     }
   } else if (warp >= 12) {
     // ===== stage-2 group: epilogue 2 (D2 -> other branches, scale, mask, activation -> TMA store) =====
@@ -476,13 +538,14 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
     const float scale = a.out_scale, aslope = a.out_slope_eff;
     const bool has_res = a.res2 != nullptr || a.res3 != nullptr;
     RingPos dr(ND), sr(a.NSTG);
-    TilePos tp(blockIdx.x, gridDim.x, a.tiles_per_item);
+    TilePos tp(first_tile, tile_step, a.tiles_per_item);
     for (int i = 0; i < n_local; ++i, dr.next(), tp.next()) {
       const int b = tp.b, tt = tp.tt;
       const int db = dr.idx;
       const int o0 = tt * a.R_out;
       int len_b = a.L;
-      if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
+      if (b >= a.B) len_b = 0;                                   // the padding tile of an odd pair
+      else if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
       mbar_wait(d2_full(db), dr.ph);
       tc_fence_after();
       if (warp == 12 && lane == 0) RP_TRACE(11, i);
@@ -508,7 +571,7 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
             tc_ld16(tcol + (uint32_t)cb, r[0]);
             tc_ld16(tcol + (uint32_t)(cb + 16), r[1]);
             uint4 g2[4], g3[4];
-            const bool add_res = has_res && o < a.R_out && grow < a.L;
+            const bool add_res = has_res && o < a.R_out && grow < a.L && b < a.B;
             if (add_res) {
               const long long rrow = (long long)b * a.L + grow;
               if (a.res2 != nullptr) {
@@ -584,15 +647,39 @@ resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync();     // the peer may still multicast commits into this CTA / read its operands
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
 template <int C, bool BF16>
+__global__ void __launch_bounds__(RP_THREADS, 1)
+resblock_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairArgs a) {
+  resblock_pair_body<C, BF16, false>(maps, a);
+}
+template <int C, bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
+resblock_pair2_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairArgs a) {
+  resblock_pair_body<C, BF16, true>(maps, a);
+}
+
+template <int C, bool BF16>
+static int launch_pair2(const PairMaps& maps, const PairArgs& a, size_t smem, cudaStream_t st) {
+  ASB_SMEM_OPT_IN(227 * 1024, resblock_pair2_kernel<C, BF16>);
+  int clusters = num_sms() / 2;
+  const int slots = (a.total_tiles + 1) / 2;
+  if (clusters > slots) clusters = slots;
+  ASB_CUDA(launch_k(resblock_pair2_kernel<C, BF16>, 2 * clusters, RP_THREADS, smem, st, maps, a));
+  return AS_OK;
+}
+
+template <int C, bool BF16>
 static int launch_pair(const PairMaps& maps, const PairArgs& a, size_t smem, cudaStream_t st) {
+  if (a.pair) return launch_pair2<C, BF16>(maps, a, smem, st);
   ASB_SMEM_OPT_IN(227 * 1024, resblock_pair_kernel<C, BF16>);
   int grid = num_sms();
   static const int grid_cap = getenv("ASB_PAIR_GRID") ? atoi(getenv("ASB_PAIR_GRID")) : 0;   // experiments: leave SMs to concurrent streams
@@ -665,15 +752,25 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   int best_found = 0;
   const int mode_lo = env_int("ASB_PAIR_MODE", 0);
   const int nt_force = env_int("ASB_PAIR_NT", -1);
+  // CTA pairs (cta_group::2): each CTA holds half of every weight block.  Needs at least two tiles and the
+  // separate-operand-buffer mode (the peer CTA's epilogue group cannot wait on the leader's x_full barrier).
+  // Measured (profiles/r02_pair_2cta_ab.txt, same-run A/B): the MMA phases get 34 % faster (59 vs 89 cycles per
+  // instruction at N = 128), but every cross-CTA hand-off that publishes memory costs ~1300 cycles (cluster-scope
+  // release on the remote arrive; TMEM-only hand-offs arrive relaxed), so the pair pays off only where a tile carries
+  // enough MMA work: C = 64: k = 7 -19 %, k = 11 -5 %; C = 128: k = 7 -2 %, k = 11 -4 %; slower for k = 3 and C = 32.
+  // ASB_PAIR_2CTA = 0 / 1 forces it off / on (where a plan fits).
+  const int pair_env = env_int("ASB_PAIR_2CTA", -1);
+  a.pair = (pair_env >= 0 ? pair_env != 0 : (C >= 64 && k >= 7)) && a.total_tiles >= 2 ? 1 : 0;
   auto fits = [&](int nx, int nt, int nstg, int sw, int s1, int s2) {
-    return pair_smem(C, a.HA, k, nx, nt, nstg, sw, s1, s2).total <= cap;
+    return pair_smem(C, a.HA, k, nx, nt, nstg, sw, s1, s2, a.pair).total <= cap;
   };
-  for (int nt = (C <= 64 ? 2 : 0); nt >= 0 && !best_found; --nt) {
+  for (int nt = ((C <= 64 || a.pair) ? 2 : 0); nt >= (a.pair ? 1 : 0) && !best_found; --nt) {
     if (nt_force >= 0 && nt != nt_force) continue;
     for (int mode = mode_lo; mode < 3 && !best_found; ++mode) {   // 0: resident, 1: conv1 streamed, 2: both streamed
       a.stream1 = mode >= 1; a.stream2 = mode >= 2;
       for (int nx = 2; nx >= 1 && !best_found; --nx) {
-        if (nx == 1 && (mode == 0 || nt > 0)) continue;   // prefer streaming / fewer operand buffers over one input buffer
+        if (nx == 1 && (mode == 0 || (nt > 0 && C <= 64))) continue;   // prefer streaming / fewer operand buffers over one input buffer
+                                                                       // (C = 128 in pair mode only fits one input + one operand buffer)
         a.NX = nx; a.NT = nt; a.NSTG = 1;
         a.SW = mode == 0 ? 0 : 3;
         if (!fits(a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2)) continue;
@@ -689,6 +786,14 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
       }
     }
   }
+  if (!best_found && a.pair) {      // no separate-buffer plan fits: single-CTA kernel with the operand in place
+    a.pair = 0;
+    for (int mode = 1; mode < 3 && !best_found; ++mode)
+      for (int nx = 2; nx >= 1 && !best_found; --nx) {
+        a.stream1 = 1; a.stream2 = mode >= 2; a.NX = nx; a.NT = 0; a.NSTG = 1; a.SW = 3;
+        if (fits(a.NX, 0, 1, a.SW, a.stream1, a.stream2)) best_found = 1;
+      }
+  }
   if (!best_found) {
     a.stream1 = a.stream2 = 1; a.NX = 1; a.NT = 0; a.NSTG = 1; a.SW = 2;
     ASB_REQUIRE(fits(1, 0, 1, 2, 1, 1), AS_ERR_SHAPE, "as_hifigan_resblock_pair: tile does not fit in shared memory");
@@ -700,16 +805,17 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   a.pipelined = (a.ND == 2 && a.NX >= 2) ? 1 : 0;
   a.pipelined = env_int("ASB_PAIR_PIPE", a.pipelined);
   if (a.ND < 2 || a.NX < 2) a.pipelined = 0;
-  const PairSmem sp = pair_smem(C, a.HA, k, a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2);
+  const PairSmem sp = pair_smem(C, a.HA, k, a.NX, a.NT, a.NSTG, a.SW, a.stream1, a.stream2, a.pair);
+  ASB_REQUIRE(!(a.pair && a.NT == 0), AS_ERR_SHAPE, "as_hifigan_resblock_pair: CTA pairs need separate operand buffers");
   ASB_REQUIRE(sp.total <= cap && a.NX >= 1 && a.NX <= 8 && a.NT >= 0 && a.NT <= 2 && a.NSTG >= 1 && a.NSTG <= 2 && a.SW <= 16 &&
                   (!(a.stream1 || a.stream2) || a.SW >= 2),
               AS_ERR_SHAPE, "as_hifigan_resblock_pair: invalid shared-memory plan (%u bytes)", sp.total);
   if (env_int("ASB_PAIR_VERBOSE", 0))
-    fprintf(stderr, "pair C=%d k=%d dil=%d: NX=%d NT=%d ND=%d NSTG=%d SW=%d stream=%d%d pipelined=%d smem=%u\n", C, k, p->dil,
-            a.NX, a.NT, a.ND, a.NSTG, a.SW, a.stream1, a.stream2, a.pipelined, sp.total);
+    fprintf(stderr, "pair C=%d k=%d dil=%d: 2cta=%d NX=%d NT=%d ND=%d NSTG=%d SW=%d stream=%d%d pipelined=%d smem=%u\n", C, k, p->dil,
+            a.pair, a.NX, a.NT, a.ND, a.NSTG, a.SW, a.stream1, a.stream2, a.pipelined, sp.total);
 
   const uint32_t fmt = (p->dtype == AS_BF16) ? 1u : 0u;
-  a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(C >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(C >> 3) << 17) | (uint32_t((a.pair ? 256 : 128) >> 4) << 24);
   a.b1 = p->b1; a.b2 = p->b2;
   a.res2 = p->res2; a.res2_ld = p->res2_ld; a.res3 = p->res3; a.res3_ld = p->res3_ld;
   a.slope = p->slope; a.inv_slope = 1.0f / p->slope;
@@ -733,7 +839,7 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   auto mkw = [&](CUtensorMap* m, const void* ptr) -> bool {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)k * C};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BKC, (cuuint32_t)C};
+    cuuint32_t box[2] = {(cuuint32_t)BKC, (cuuint32_t)(a.pair ? C / 2 : C)};   // pair mode: each CTA loads its half of a block
     cuuint32_t es[2] = {1, 1};
     return enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from artspeech_b200 import ops
 
-KNOBS = ("ASB_PAIR_NX", "ASB_PAIR_NSTG", "ASB_PAIR_PIPE", "ASB_PAIR_SW", "ASB_PAIR_MODE", "ASB_PAIR_DBG")
+KNOBS = ("ASB_PAIR_NX", "ASB_PAIR_NSTG", "ASB_PAIR_PIPE", "ASB_PAIR_SW", "ASB_PAIR_MODE", "ASB_PAIR_DBG", "ASB_PAIR_2CTA")
 
 
 def run(C, L, k, dil, env, reps=5, B=16):
@@ -40,7 +40,10 @@ def run(C, L, k, dil, env, reps=5, B=16):
 
 def main():
     only = [int(v) for v in sys.argv[1:]]
-    if os.environ.get("EXP") == "ab":
+    if os.environ.get("EXP") == "2cta":
+        names = ["2cta", "1cta", "2cta", "1cta"]
+        variants = [{"ASB_PAIR_2CTA": "1"}, {"ASB_PAIR_2CTA": "0"}, {"ASB_PAIR_2CTA": "1"}, {"ASB_PAIR_2CTA": "0"}]
+    elif os.environ.get("EXP") == "ab":
         names = ["fast", "nofast", "fast", "nofast"]
         variants = [{}, {"ASB_PAIR_DBG": "64"}, {}, {"ASB_PAIR_DBG": "64"}]
     elif os.environ.get("EXP") == "dbg":

@@ -23,6 +23,34 @@ def test_lpt_sharding_balances_and_covers():
     assert engine.shard_utterances([5.0], 2) == [[0], []]
 
 
+def test_length_contiguous_sharding_keeps_padding_flat():
+    """engine.shard_by_length on the config-5 length distribution: a partition, cost-balanced within a few per cent,
+    and -- unlike LPT on frame counts -- the padded work per frame does not grow with the number of ranks."""
+    g = torch.Generator().manual_seed(1)
+    frames = (torch.randint(15, 595, (512,), generator=g) * 5.3).long().tolist()
+    q = lambda f: (f + 79) // 80 * 80
+
+    def padded(shard):
+        f = [frames[i] for i in shard]
+        return sum(len(b) * q(max(f[i] for i in b)) for b in engine.bucket_utterances(f, 16, 25600, quantum=80))
+    base = padded(list(range(512))) / sum(frames)
+    for world in (1, 2, 4, 8):
+        shards = engine.shard_by_length(frames, world)
+        assert sorted(i for s in shards for i in s) == list(range(512))
+        cost = [padded(s) + 280 * len(s) for s in shards]
+        assert max(cost) <= 1.08 * sum(cost) / world
+        assert sum(padded(s) for s in shards) / sum(frames) <= base + 0.02
+        lpt = engine.shard_utterances(frames, world)
+        if world == 8:
+            assert sum(padded(s) for s in lpt) / sum(frames) >= base + 0.15      # what it replaces
+        # contiguous in length: every utterance of rank r is at least as long as every utterance of rank r + 1
+        for a, b in zip(shards, shards[1:]):
+            if a and b:
+                assert min(frames[i] for i in a) >= max(frames[i] for i in b)
+    assert engine.shard_by_length([], 3) == [[], [], []]
+    assert sorted(i for s in engine.shard_by_length([100, 50], 4) for i in s) == [0, 1]
+
+
 def test_length_bucketed_micro_batches():
     """engine.bucket_utterances on the BASELINE config-5 length distribution: every utterance exactly once, batch and
     padded-frame budgets respected, little padding."""

@@ -42,7 +42,7 @@ def test_length_contiguous_sharding_keeps_padding_flat():
         assert sum(padded(s) for s in shards) / sum(frames) <= base + 0.02
         lpt = engine.shard_utterances(frames, world)
         if world == 8:
-            assert sum(padded(s) for s in lpt) / sum(frames) >= base + 0.15      # what it replaces
+            assert sum(padded(s) for s in lpt) / sum(frames) >= base + 0.10      # what it replaces (uniform lengths: +15 %; the long-tailed config-5 lengths: +28 %)
         # contiguous in length: every utterance of rank r is at least as long as every utterance of rank r + 1
         for a, b in zip(shards, shards[1:]):
             if a and b:

@@ -113,6 +113,7 @@ class StyleEncoder(nn_util.PlanMixin, nn.Module):
         self.Energylinear = nn.Linear(2 * d, style_dim // 4)
         self.style_dim = style_dim
         self.compute_dtype = torch.float16
+        self._znorm_consts = {}
         self._init_plan()
 
     def _build_plan(self, device):
@@ -140,8 +141,13 @@ class StyleEncoder(nn_util.PlanMixin, nn.Module):
         # z-normalisation with the dataset statistics (:447-449)
         def znorm(x_cl, mean, std):
             C = x_cl.shape[-1]
-            sub = mean.to(dev).float().reshape(-1).expand(C).contiguous()
-            mul = (1.0 / std.to(dev).float().reshape(-1)).expand(C).contiguous()
+            key = (id(mean), id(std), C, str(dev))
+            cached = self._znorm_consts.get(key)
+            if cached is None or cached[2] is not mean or cached[3] is not std:    # per-channel constants, built once
+                sub = mean.to(dev).float().reshape(-1).expand(C).contiguous()
+                mul = (1.0 / std.to(dev).float().reshape(-1)).expand(C).contiguous()
+                cached = self._znorm_consts[key] = (sub, mul, mean, std)
+            sub, mul = cached[0], cached[1]
             cf = ops.to_channels_first(x_cl, torch.float32, sub=sub, mul=mul)           # [B,C,T]
             return cf, ops.to_channels_last(cf, torch.float32)
 

@@ -223,6 +223,16 @@ class Generator(nn.Module):
         dt = self.compute_dtype
         B, T, _ = mel_cl.shape
         lens = None if lengths is None else lengths.to(device=dev, dtype=torch.int32)
+        # per-stage lengths (frames x 10, x 50, x 150, x 300) in ONE elementwise launch instead of one per stage
+        stage_lens = None
+        if lens is not None:
+            if plan.get("rates") is None or plan["rates"].device != dev:
+                cum, r = [], 1
+                for u in self.h.upsample_rates:
+                    r *= u
+                    cum.append(r)
+                plan["rates"] = torch.tensor(cum, dtype=torch.int32, device=dev).view(-1, 1)
+            stage_lens = lens.view(1, -1) * plan["rates"]
 
         # conv_pre, storing leaky_relu(x, 0.1): the only consumer is ups[0] (vocoder.py:101-104)
         _, a = ops.conv(mel_cl, plan["pre"], act_out=dt, act=ops.ACT_LRELU, slope=LRELU_SLOPE, lens=lens)
@@ -243,7 +253,7 @@ class Generator(nn.Module):
                 L = L * u
                 xa = xa.view(B, L, cout)
                 if lens is not None:
-                    lens = lens * u
+                    lens = stage_lens[i]
                 done = []          # raw outputs of finished branches
                 for j in range(self.num_kernels):
                     blk = self.resblocks[i * self.num_kernels + j]
@@ -267,7 +277,7 @@ class Generator(nn.Module):
             xr = xr.view(B, L, cout)
             xa = xa.view(B, L, cout)
             if lens is not None:
-                lens = lens * u
+                lens = stage_lens[i]
             xs = None          # running sum of finished MRF branches (residual stream dtype)
             for j in range(self.num_kernels):
                 c1s, c2s = plan["res"][i * self.num_kernels + j]

@@ -31,6 +31,7 @@ struct ConvArgs {
   int halo_rows, pad_lo;   // halo variants: rows of the halo tile, -min(tap_dt)
   int epi_tma;             // 1: all-16-bit 1-D epilogue through shared memory + TMA
   int halo_baseoff;        // swizzled halo: put (row & 7) into the descriptor's base-offset field
+  int skip;                // 1: tiles that lie entirely beyond their item's length are left out (conv_igemm / 2cta only)
 };
 
 struct EpiMaps { CUtensorMap r1, raw, act; };
@@ -40,6 +41,53 @@ __host__ __device__ constexpr uint32_t epi_cols(int bn) { return bn >= 64 ? 64u 
 __host__ __device__ constexpr uint32_t epi_warp_bytes(int bn) { return 2u * 32u * epi_cols(bn) * 2u; }
 __host__ __device__ constexpr uint32_t epi_bytes(int bn) { return 8u * epi_warp_bytes(bn) + 64u; }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tile skipping for ragged batches: an M-tile whose first time index is >= its item's length produces only zeros
+// (the epilogue masks rows t >= lens[b]).  Producer, MMA issuer and epilogue evaluate the same pure function of
+// (tile, lens) and leave such tiles out of the pipeline -- no ring slot, accumulator stage or barrier phase is
+// consumed -- and the epilogue's first warpgroup writes the zeros.  A 2-CTA super-tile is skipped only when both
+// of its M-tiles are dead.  Batches with predicted durations / mixed-length serving otherwise compute their padding.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool conv_mtile_dead(const ConvArgs& a, int mt) {
+  const int m = mt / a.n_ftiles;
+  const int tt = m % a.n_ttiles, b = m / a.n_ttiles;
+  if (b >= a.B) return true;                       // the filler tile of an odd pair
+  return tt * a.tT >= __ldg(a.lens + b);
+}
+__device__ __forceinline__ bool conv_unit_skip(const ConvArgs& a, int unit, int cl) {
+  if (!a.skip) return false;
+  for (int r = 0; r < cl; ++r)
+    if (!conv_mtile_dead(a, unit * cl + r)) return false;
+  return true;
+}
+// zeros for `ncols` channels of one output row (any output dtype / alignment)
+__device__ __forceinline__ void conv_zero_row(void* base, int dtype, long long off_elems, int ncols) {
+  const int es = dtype == AS_F32 ? 4 : 2;
+  char* p = reinterpret_cast<char*>(base) + off_elems * es;
+  const int nbytes = ncols * es;
+  int i = 0;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+    for (; i + 16 <= nbytes; i += 16) *reinterpret_cast<uint4*>(p + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (; i < nbytes; i += es) {
+    if (es == 4) *reinterpret_cast<float*>(p + i) = 0.f;
+    else *reinterpret_cast<uint16_t*>(p + i) = 0;
+  }
+}
+// the epilogue's share of a skipped tile: this thread's row (tile row m = q * 32 + lane) of the CTA's own M-tile
+__device__ __forceinline__ void conv_zero_tile_row(const ConvArgs& a, int mt, int n0, int bn, int m) {
+  const int it_ = m / a.tF, if_ = m - it_ * a.tF;
+  int u = mt;
+  const int ft = u % a.n_ftiles; u /= a.n_ftiles;
+  const int tt = u % a.n_ttiles; u /= a.n_ttiles;
+  const int b = u, t = tt * a.tT + it_, f = ft * a.tF + if_;
+  if (b >= a.B || t >= a.To || f >= a.Fo) return;
+  const int ncols = min(bn, a.Cout - n0);
+  if (ncols <= 0) return;
+  const long long row = ((long long)b * a.To + t) * a.Fo + f;
+  if (a.y_raw != nullptr) conv_zero_row(a.y_raw, a.y_raw_dtype, row * a.y_raw_ld + n0, ncols);
+  if (a.y_act != nullptr) conv_zero_row(a.y_act, a.y_act_dtype, row * a.y_act_ld + n0, ncols);
+}
 
 // ---------------------------------------------------------------------------------------------
 // epilogue store helpers: 16 consecutive channels of one row
@@ -167,8 +215,13 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
   const int q = warp & 3;          // TMEM lane quadrant this warp may access
   const int m = q * 32 + lane;     // tile row
   const int it_ = m / a.tF, if_ = m - it_ * a.tF;
-  int lt = 0;
-  for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++lt) {
+  int lt_live = 0;
+  for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    if (conv_unit_skip(a, tile % m_tiles, cl)) {           // all padding: zeros, no accumulator stage consumed
+      if (wg == 0) conv_zero_tile_row(a, (tile % m_tiles) * cl + rank, (tile / m_tiles) * BN, BN, m);
+      continue;
+    }
+    const int lt = lt_live++;
     if ((lt & 1) != wg) continue;
     int mt = (tile % m_tiles) * cl + rank;
     const int n0 = (tile / m_tiles) * BN;
@@ -305,8 +358,13 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
   // 16-byte unit swizzle of the TMA layout: 128B mode XORs with (row & 7), 64B mode with (row >> 1) & 3
   const uint32_t sw = (EPC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
   uint32_t rphase = 0;
-  int lt = 0;
-  for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++lt) {
+  int lt_live = 0;
+  for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    if (conv_unit_skip(a, tile % m_tiles, cl)) {           // all padding: zeros (plain stores), no accumulator stage consumed
+      if (wg == 0) conv_zero_tile_row(a, (tile % m_tiles) * cl + rank, (tile / m_tiles) * BN, BN, q * 32 + lane);
+      continue;
+    }
+    const int lt = lt_live++;
     if ((lt & 1) != wg) continue;
     const int mt = (tile % m_tiles) * cl + rank;
     const int n0 = (tile / m_tiles) * BN;
@@ -464,6 +522,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ===== TMA producer =====
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (conv_unit_skip(a, tile % m_tiles, 1)) continue;
         int mt = tile % m_tiles;
         const int n0 = (tile / m_tiles) * BN;
         const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
@@ -485,7 +544,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (elect_one()) {   // elected lane of a converged warp: back-to-back UTCHMMA issue (no per-instruction election loop)
       // ===== MMA issuer =====
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (conv_unit_skip(a, tile % m_tiles, 1)) continue;
         const int acc = lt & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue drained this stage
         tc_fence_after();
@@ -506,6 +566,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
         }
         tc_commit(tfull_bar(acc));  // accumulator of this tile complete
+        ++lt;
       }
     }
   } else {
@@ -599,6 +660,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // ===== TMA producer (both CTAs): own activation rows + own half of the weight tile =====
       int it = 0;
       for (int st = cid; st < total_super; st += n_clusters) {
+        if (conv_unit_skip(a, st % m_pairs, 2)) continue;
         int mt = (st % m_pairs) * 2 + (int)rank;
         const int n0 = (st / m_pairs) * BN;
         const int ft = mt % a.n_ftiles; mt /= a.n_ftiles;
@@ -621,7 +683,8 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (leader && elect_one()) {
       // ===== MMA issuer (leader CTA only) =====
       int it = 0, lt = 0;
-      for (int st = cid; st < total_super; st += n_clusters, ++lt) {
+      for (int st = cid; st < total_super; st += n_clusters) {
+        if (conv_unit_skip(a, st % m_pairs, 2)) continue;
         const int acc = lt & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)lt >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -640,6 +703,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc2_commit(empty_bar(s));
         }
         tc2_commit(tfull_bar(acc));
+        ++lt;
       }
     }
     __syncwarp();
@@ -961,6 +1025,8 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const EpiMaps& e
   if (stages > 10) stages = 10;
   if (stages < 2) stages = 2;
   a.stages = stages;
+  static const bool no_skip = getenv("ASB_CONV_NO_SKIP") != nullptr;
+  a.skip = (a.lens != nullptr && !no_skip) ? 1 : 0;     // ragged batches: tiles beyond an item's length are left out
   const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
                       (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
   ASB_SMEM_OPT_IN(227 * 1024, conv_igemm_kernel<BN, BK, BF16>);
@@ -981,6 +1047,8 @@ int launch_conv_2cta(const CUtensorMap& tmA, const CUtensorMap& tmWh, const EpiM
   if (stages < 2) stages = 2;
   a.stages = stages;
   a.idesc = (a.idesc & ~(0x1Fu << 24)) | (uint32_t(256 >> 4) << 24);      // UMMA M = 256 across the CTA pair
+  static const bool no_skip = getenv("ASB_CONV_NO_SKIP") != nullptr;
+  a.skip = (a.lens != nullptr && !no_skip) ? 1 : 0;
   const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
                       (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
   ASB_SMEM_OPT_IN(227 * 1024, conv_igemm_2cta_kernel<BK, BF16>);
@@ -998,7 +1066,7 @@ int launch_halo(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, EncodeT
   int lo = 0, hi = 0;
   for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
   const int HRP = (128 + hi - lo + 7) / 8 * 8;
-  a.kchunks = KC; a.halo_rows = HRP; a.pad_lo = -lo;
+  a.kchunks = KC; a.halo_rows = HRP; a.pad_lo = -lo; a.skip = 0;
   a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;
   const size_t a_bytes = (size_t)KC * HRP * 16, w_bytes = (size_t)p->ntaps * KC * BN * 16;
   int stages = 4;
@@ -1048,7 +1116,7 @@ int launch_halo_sw(const as_conv_params* p, ConvArgs& a, const EpiMaps& em, Enco
   int lo = 0, hi = 0;
   for (int j = 0; j < p->ntaps; ++j) { lo = p->tap_dt[j] < lo ? p->tap_dt[j] : lo; hi = p->tap_dt[j] > hi ? p->tap_dt[j] : hi; }
   const int HRP = (128 + hi - lo + 7) / 8 * 8;
-  a.kchunks = KCH; a.halo_rows = HRP; a.pad_lo = -lo;
+  a.kchunks = KCH; a.halo_rows = HRP; a.pad_lo = -lo; a.skip = 0;
   static const int baseoff_mode = getenv("ASB_HALO_BASEOFF") ? atoi(getenv("ASB_HALO_BASEOFF")) : 0;
   a.halo_baseoff = baseoff_mode;
   a.tT = 128; a.tF = 1; a.n_ttiles = (p->To + 127) / 128; a.n_ftiles = 1;

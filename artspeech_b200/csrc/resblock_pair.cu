@@ -50,7 +50,8 @@ struct PairArgs {
   int pair;  // 1: cluster of two CTAs, tcgen05.mma.cta_group::2 (each CTA holds half of every weight block)
   int NT;    // stage-2 operand buffers: 0 = written in place over the input tile, 1..2 = separate buffers (the
              // input tile is then released as soon as stage 1 and the residual read are done)
-  int dbg;   // timing experiments only (ASB_PAIR_DBG; results are wrong): 1 no MMAs, 2 no stores, 4 no reloads, 8 no epilogue-1 math, 16 no seed
+  int dbg;   // timing experiments only (ASB_PAIR_DBG; results are wrong): 1 no MMAs, 2 no stores, 4 no reloads, 8 no epilogue-1 math, 16 no seed;
+             // 64 no epilogue fast paths, 128 no tile skipping (results stay correct)
   uint32_t idesc;
   const float* b1;
   const float* b2;
@@ -58,6 +59,7 @@ struct PairArgs {
   const void* res3; long long res3_ld;
   float slope, inv_slope, out_scale, out_slope_eff;
   const int* lens;
+  void* y; long long y_ld;    // raw output pointer: skipped tiles are zero-filled with plain stores
 };
 struct PairMaps { CUtensorMap x, w1, w2, y, y_tail; };
 
@@ -190,6 +192,22 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
     if (PAIR) tc2_commit(bar);
     else tc_commit(bar);
   };
+  // ---- tile skipping: a tile whose first output row lies beyond its utterance's length produces only zeros.  Every
+  // role evaluates the same pure function of (tile, lens) and leaves such tiles out of the pipeline altogether (no
+  // barrier, ring position or buffer is touched); the drain group zero-fills their rows.  In pair mode the two CTAs'
+  // adjacent tiles are skipped together or not at all.  Ragged batches (predicted durations, mixed-length serving)
+  // otherwise compute their padding: every kernel masks by length, none skipped.
+  const bool can_skip = a.lens != nullptr && !(a.dbg & 128);
+  auto len_of = [&](int b) { return b >= a.B ? 0 : (a.lens != nullptr ? min(__ldg(a.lens + b), a.L) : a.L); };
+  auto dead = [&](int b, int tt) { return tt * a.R_out >= len_of(b); };          // own tile is all padding (or the odd pair's filler)
+  auto skip_tile = [&](const TilePos& tp) {
+    if (!can_skip) return false;
+    if (!dead(tp.b, tp.tt)) return false;
+    if (!PAIR) return true;
+    int pb = tp.b, pt = tp.tt + (leader ? 1 : -1);                                // the partner's tile
+    if (pt >= a.tiles_per_item) { pt = 0; ++pb; } else if (pt < 0) { pt = a.tiles_per_item - 1; --pb; }
+    return dead(pb, pt);
+  };
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bias_s[i] = i < C ? a.b1[i] : a.b2[i - C];
 
   if (threadIdx.x == 0) {
@@ -244,20 +262,25 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
       // ===== relay (pair mode): x_full lives in the leader only; tell both CTAs' epilogue groups that tile i landed.
       // A thread of its own because the cluster-scope release of the remote arrive stalls its issuer for ~1300 cycles.
       RingPos xr(NX);
-      for (int i = 0; i < n_local; ++i, xr.next()) {
+      TilePos tp(first_tile, tile_step, a.tiles_per_item);
+      for (int i = 0; i < n_local; ++i, tp.next()) {
+        if (skip_tile(tp)) continue;
         mbar_wait(x_full(xr.idx), xr.ph);
         mbar_arrive(x_seen(xr.idx));
         mbar_arrive_cluster(mapa_u32(x_seen(xr.idx), 1));
+        xr.next();
       }
     }
     if (lane == 0) {
       // ===== activation-tile producer =====
       RingPos xr(NX);
       TilePos tp(first_tile, tile_step, a.tiles_per_item);
-      for (int i = 0; i < n_local; ++i, xr.next(), tp.next()) {
+      for (int i = 0; i < n_local; ++i, tp.next()) {
+        if (skip_tile(tp)) continue;
         const int b = tp.b, tt = tp.tt;
         const int xb = xr.idx;
         const uint32_t ph = xr.ph;
+        xr.next();
         mbar_wait(x_empty(xb), ph ^ 1u);
         RP_TRACE(0, i);
         if ((a.dbg & 4) && i >= NX) { if (leader) mbar_arrive(x_full(xb)); continue; }
@@ -305,15 +328,15 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
             else tma_load_2d(ring + slot * WBLK, wm, wr_full(slot), (j % KCH) * BKC, (j / KCH) * C);
           }
         };
-        if (a.pipelined) {
-          if (n_local > 0) feed(0);
-          for (int i = 0; i < n_local; ++i) {
-            if (i + 1 < n_local) feed(0);
-            feed(1);
-          }
-        } else {
-          for (int i = 0; i < n_local; ++i) { feed(0); feed(1); }
+        TilePos tp(first_tile, tile_step, a.tiles_per_item);
+        bool pending = false;                  // a live tile whose stage 2 has not been fed yet (pipelined order)
+        for (int i = 0; i < n_local; ++i, tp.next()) {
+          if (skip_tile(tp)) continue;
+          feed(0);
+          if (a.pipelined) { if (pending) feed(1); pending = true; }
+          else feed(1);
         }
+        if (pending) feed(1);
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -397,17 +420,17 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
         if (mt == 0) RP_TRACE(4, i);
         x2.next(); d2.next(); t2.next();
       };
-      if (a.pipelined) {
-        // stage 1 of tile i+1 is issued before stage 2 of tile i: the tensor pipe works on it while
-        // warpgroup 0 converts tile i's accumulator into the stage-2 operand
-        if (n_local > 0) issue1(0);
-        for (int i = 0; i < n_local; ++i) {
-          if (i + 1 < n_local) issue1(i + 1);
-          issue2(i);
-        }
-      } else {
-        for (int i = 0; i < n_local; ++i) { issue1(i); issue2(i); }
+      // pipelined: stage 1 of the next live tile is issued before stage 2 of the current one -- the tensor pipe
+      // works on it while epilogue group 1 converts this tile's accumulator into the stage-2 operand
+      TilePos tp(first_tile, tile_step, a.tiles_per_item);
+      int pending = -1;
+      for (int i = 0; i < n_local; ++i, tp.next()) {
+        if (skip_tile(tp)) continue;
+        issue1(i);
+        if (a.pipelined) { if (pending >= 0) issue2(pending); pending = i; }
+        else issue2(i);
       }
+      if (pending >= 0) issue2(pending);
     }
     __syncwarp();
   } else if (warp >= 4 && warp < 12) {
@@ -417,7 +440,8 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
     const float slope = a.slope, inv_slope = a.inv_slope;
     RingPos xr(NX), dr(ND), tr(NT ? NT : 1);
     TilePos tp(first_tile, tile_step, a.tiles_per_item);
-    for (int i = 0; i < n_local; ++i, xr.next(), dr.next(), tr.next(), tp.next()) {
+    for (int i = 0; i < n_local; ++i, tp.next()) {
+      if (skip_tile(tp)) continue;
       const int b = tp.b, tt = tp.tt;
       const int xb = xr.idx, db = dr.idx;
       const int o0 = tt * a.R_out;
@@ -528,6 +552,7 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
       // With a single accumulator set (C = 128) the D2 buffer is free long before stage 1 ends: seed first, under
       // stage 1's MMAs.
       if (NT && ND == 2) { epi1(); seed(); } else { seed(); epi1(); }
+      xr.next(); dr.next(); tr.next();
     }
   } else if (warp >= 12) {
     // ===== stage-2 group: epilogue 2 (D2 -> other branches, scale, mask, activation -> TMA store) =====
@@ -539,10 +564,22 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
     const bool has_res = a.res2 != nullptr || a.res3 != nullptr;
     RingPos dr(ND), sr(a.NSTG);
     TilePos tp(first_tile, tile_step, a.tiles_per_item);
-    for (int i = 0; i < n_local; ++i, dr.next(), tp.next()) {
+    for (int i = 0; i < n_local; ++i, tp.next()) {
       const int b = tp.b, tt = tp.tt;
-      const int db = dr.idx;
       const int o0 = tt * a.R_out;
+      if (skip_tile(tp)) {
+        // all padding: zero this warp's 32 rows (16-byte stores, a row's units on adjacent lanes)
+        if (b < a.B) {
+          constexpr int U = C / 8;                              // 16-byte units per row
+          const int r0 = o0 + mt * 128 + q * 32;
+          const int nrows = min(32, min(a.R_out - (mt * 128 + q * 32), a.L - r0));
+          uint16_t* yb = reinterpret_cast<uint16_t*>(a.y) + ((long long)b * a.L + r0) * a.y_ld;
+          for (int idx = lane; idx < nrows * U; idx += 32)
+            *reinterpret_cast<uint4*>(yb + (long long)(idx / U) * a.y_ld + (idx % U) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
+      }
+      const int db = dr.idx;
       int len_b = a.L;
       if (b >= a.B) len_b = 0;                                   // the padding tile of an odd pair
       else if (a.lens != nullptr) len_b = min(__ldg(a.lens + b), a.L);
@@ -642,6 +679,7 @@ __device__ __forceinline__ void resblock_pair_body(const PairMaps& maps, const P
       __syncwarp();
       if (lane == 0) mbar_arrive(d2_empty(db));
       if (warp == 12 && lane == 0) RP_TRACE(12, i);
+      dr.next();
     }
     if (lane == 0) bulk_wait_all0();
   }
@@ -822,6 +860,7 @@ extern "C" int as_hifigan_resblock_pair(const as_resblock_pair_params* p, void* 
   a.out_scale = p->out_scale;
   a.out_slope_eff = p->out_act == AS_ACT_LRELU ? p->out_slope : 1.0f;
   a.lens = p->lens;
+  a.y = p->y; a.y_ld = p->y_ld;
   a.dbg = env_int("ASB_PAIR_DBG", 0);
 
   const CUtensorMapDataType dt = p->dtype == AS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;

@@ -60,6 +60,13 @@ class Synthesizer:
     the predictor still runs inside that graph (its output is returned in ``last["duration"]`` /
     ``last["pred_dur"]``) while the given durations drive the length regulator.
 
+    ``duration_bound`` (half-rate frames per token, e.g. 4.0 = 0.1 s per phoneme) removes that hand-off as well: with
+    predicted durations the WHOLE pass is then one graph whose frame bucket is ``tokens * duration_bound`` -- every
+    tensor-core kernel on the path leaves out the tiles beyond an utterance's predicted length, so the generous
+    bucket costs zero-fill writes, not compute -- and the frame counts come back with the waveforms
+    (``last["frames"]`` is None, ``last["pred_sum"]`` / the returned ``mel_lengths`` are device tensors; an
+    utterance whose prediction exceeds the bound is truncated there, ``synthesize_many`` re-runs those exactly).
+
     ``pipeline_depth`` > 1 keeps that many calls in flight: call ``i`` runs on side stream ``i % depth`` with its own
     graph instances and buffers, so the latency-bound acoustic model of one batch overlaps the throughput-bound
     vocoder of the previous one.  The outputs of a call are produced on ``last_stream``: consume them there (``with
@@ -71,7 +78,8 @@ class Synthesizer:
 
     def __init__(self, model, generator, device="cuda:0", use_cuda_graph: bool = True, pipeline_depth: int = 1,
                  pcm16: bool = False, acoustic_sms: Optional[int] = None, token_quantum: int = 32,
-                 frame_quantum: int = 40, max_graphs: int = 48, capture_after: int = 1):
+                 frame_quantum: int = 40, max_graphs: int = 48, capture_after: int = 1,
+                 duration_bound: Optional[float] = None):
         self.device = torch.device(device)
         self.pcm16 = bool(pcm16)
         # SM split between the two phases when batches overlap: the acoustic model's persistent kernels are sized
@@ -82,6 +90,7 @@ class Synthesizer:
         self.pipeline_depth = max(1, int(pipeline_depth))
         self.token_quantum, self.frame_quantum = max(1, int(token_quantum)), max(1, int(frame_quantum))
         self.max_graphs, self.capture_after = max(1, int(max_graphs)), max(1, int(capture_after))
+        self.duration_bound = None if duration_bound is None else float(duration_bound)
         self._slot_streams = None
         self._slot_done = {}
         self._calls = 0
@@ -272,14 +281,17 @@ class Synthesizer:
 
     # ---------------------------------------------------------------------------------------
     @torch.no_grad()
-    def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None, voice=None, predict_durations: bool = False):
+    def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None, voice=None, predict_durations: bool = False,
+                   exact_frames: bool = False):
         """``tokens`` int64 [B,Tt] and ``mels`` fp32 [B,80,Tr]: device tensors or (pinned) HOST tensors -- host inputs
         are copied straight into the graph's static buffers; ``tok_lens`` / ``mel_lens`` int64 [B] HOST tensors (or
         lists); ``durations`` int64 [B,Tt] HOST tensor or None (predict them, one device->host sync of B integers);
         ``voice``: cached ``encode_voice`` result (the style encoder is then skipped).
         Returns (wav [B, 300*Tm_max] fp32 or int16, mel_lengths int32 [B] (device), mel fp32 [B,80,Tm_max]) with
         ``Tm_max`` the longest utterance's frame count; per-call extras (predicted durations, frame counts) are in
-        ``self.last``."""
+        ``self.last``.  With ``duration_bound`` set and no ``durations`` the pass is sync-free: ``Tm_max`` is then the
+        bound's frame bucket and the utterances' true lengths are the returned ``mel_lengths`` (``exact_frames=True``
+        forces the two-graph path with the frame-count read-back)."""
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         self.last_stream = cur
@@ -297,8 +309,13 @@ class Synthesizer:
         if durations is not None:
             sums = [int(durations[b, :tl[b]].sum()) for b in range(B)]
         graphable = self.use_cuda_graph and all(v == Tr for v in ml)
-        key_a = ("ab" if durations is not None else "a", voice is not None, B, Tt_b, Tr, predict,
-                 _ceil_to(max(sums), self.frame_quantum) if sums is not None else 0)
+        bounded = durations is None and self.duration_bound is not None and not exact_frames
+        if bounded:
+            L_bound = _ceil_to(int(-(-Tt_b * self.duration_bound // 1)), self.frame_quantum)
+            key_a = ("abp", voice is not None, B, Tt_b, Tr, True, L_bound)
+        else:
+            key_a = ("ab" if durations is not None else "a", voice is not None, B, Tt_b, Tr, predict,
+                     _ceil_to(max(sums), self.frame_quantum) if sums is not None else 0)
         if graphable:
             n = self._seen.get(key_a, 0) + 1
             self._seen[key_a] = n
@@ -326,11 +343,19 @@ class Synthesizer:
                 def fn(ent=ent):
                     st = self._phase_a(ent.tok, ent.lens_t, ent.mels, mel_lens_dev, ml, ent.voice, predict)
                     return self._phase_b(st, ent.dur, L_b)
+            elif bounded:
+                L_b = key_a[-1]
+
+                def fn(ent=ent):
+                    st = self._phase_a(ent.tok, ent.lens_t, ent.mels, mel_lens_dev, ml, ent.voice, True)
+                    out = self._phase_b(st, st["pred_dur"], L_b)
+                    out["pred_sum"] = st["pred_sum"]
+                    return out
             else:
                 def fn(ent=ent):
                     return self._phase_a(ent.tok, ent.lens_t, ent.mels, mel_lens_dev, ml, ent.voice, True)
             ent.graph, ent.out, ent.launches = self._capture(slot, fn)
-            if durations is None:
+            if durations is None and not bounded:
                 ent.state = ent.out
                 ent.out = None
                 ent.pin_meta = torch.zeros(B * Tt_b + B, dtype=torch.int32).pin_memory()
@@ -349,7 +374,7 @@ class Synthesizer:
         with torch.cuda.stream(run_stream):
             self._stage(ent, tokens, tl, mels, durations, voice, run_stream)
             ent.graph.replay()
-            if durations is None:
+            if durations is None and not bounded:
                 # the only device->host hand-off of the pass: B frame counts (the other slot keeps the GPU busy)
                 pin_sum = ent.pin_meta[:B]
                 pin_sum.copy_(ent.state["pred_sum"], non_blocking=True)
@@ -379,6 +404,9 @@ class Synthesizer:
         self.last_stream = run_stream
         self.launches_per_call = launches
         ops._count(launches)
+        if bounded:
+            self.last = dict(out, frames=None, graph=True, frame_bound=2 * key_a[-1])
+            return out["wav"], out["mel_lengths"], out["mel"]
         Tm = 2 * max(sums)
         self.last = dict(out, frames=[2 * v for v in sums], graph=True,
                          duration=(ent.state or ent.out)["duration"], pred_dur=(ent.state or ent.out)["pred_dur"])
@@ -511,7 +539,7 @@ def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels
     arena = arena or (HostArena() if to_host else None)
     if to_host:
         arena.reset()
-    pending = []
+    pending, late = [], []
     for idx in bucket_utterances(plan_frames, max_batch, max_padded_frames, quantum=2 * syn.frame_quantum):
         Tt = max(int(tokens[i].shape[0]) for i in idx)
         Tr = max(int(ref_mels[i].shape[1]) for i in idx)
@@ -525,23 +553,46 @@ def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels
             mel[j, :, :ref_mels[i].shape[1]] = ref_mels[i]
         tl = [int(tokens[i].shape[0]) for i in idx]
         ml = [int(ref_mels[i].shape[1]) for i in idx]
-        wav, _, _ = syn.synthesize(tok, tl, mel, ml, dur)
+        wav, mel_lengths, _ = syn.synthesize(tok, tl, mel, ml, dur)
         got = syn.last["frames"]
-        for j, i in enumerate(idx):
-            frames[i] = got[j]
+        if got is not None:
+            for j, i in enumerate(idx):
+                frames[i] = got[j]
         with torch.cuda.stream(syn.last_stream):
             if to_host:
                 S = wav.shape[1]
                 dst = arena.take(len(idx) * S, dt).view(len(idx), S)
                 dst.copy_(wav, non_blocking=True)
-                for j, i in enumerate(idx):
-                    wavs[i] = dst[j, :HOP * frames[i]]
+            else:
+                dst = wav.clone() if got is None else None
+            if got is None:
+                # sync-free pass (Synthesizer(duration_bound=...)): the frame counts come back with the waveforms
+                meta = arena.take(2 * len(idx), torch.int32) if to_host else torch.empty(2 * len(idx), dtype=torch.int32).pin_memory()
+                meta[:len(idx)].copy_(mel_lengths, non_blocking=True)
+                meta[len(idx):].copy_(syn.last["pred_sum"], non_blocking=True)
+                late.append((idx, dst, meta, syn.last["frame_bound"]))
             else:
                 for j, i in enumerate(idx):
-                    wavs[i] = wav[j, :HOP * frames[i]].clone()
+                    wavs[i] = dst[j, :HOP * frames[i]] if to_host else wav[j, :HOP * frames[i]].clone()
         pending.append((tok, mel))            # pinned inputs must outlive their asynchronous copies
     syn.join()
-    if to_host:
+    if to_host or late:
+        torch.cuda.current_stream(syn.device).synchronize()
+    redo = []
+    for idx, dst, meta, bound in late:
+        for j, i in enumerate(idx):
+            frames[i] = int(meta[j])
+            wavs[i] = dst[j, :HOP * frames[i]]
+            if 2 * int(meta[len(idx) + j]) > bound:       # the prediction did not fit the bound: truncated there
+                redo.append(i)
+    for i in redo:                                         # rare: exact two-graph pass for the utterances that overflowed
+        w, _, _ = syn.synthesize(tokens[i].view(1, -1).pin_memory(), [int(tokens[i].shape[0])],
+                                 ref_mels[i].unsqueeze(0).pin_memory(), [int(ref_mels[i].shape[1])], None, exact_frames=True)
+        frames[i] = syn.last["frames"][0]
+        with torch.cuda.stream(syn.last_stream):
+            wavs[i] = w[0, :HOP * frames[i]].clone() if not to_host else w[0, :HOP * frames[i]].to("cpu")
+    if redo:
+        syn.join()
         torch.cuda.current_stream(syn.device).synchronize()
     return wavs, frames
 

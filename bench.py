@@ -384,6 +384,64 @@ def bench_config4(syn, dev, steps=3):
             "audio_s_per_s": 8 * 60.0 / (ms / 1e3), "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}
 
 
+def bench_predicted(model, gen, dev, host_sets, tok_lens, mel_lens, depth, steps):
+    """The same batches with NO durations given: graph A (encoders + duration predictor, round / clamp on the device)
+    -> read-back of 16 frame counts -> graph B (regulator, predictors, decoder, vocoder) for the frame bucket the
+    predictions land in.  Random-init weights predict ~1 half-rate frame per token, so the predictor's output bias is
+    shifted by +1.67 for this measurement only (mean 2.67 frames per token, the LibriTTS ratio of the workload: ~10 s
+    per utterance, but now different for every utterance and step); run last, the weights are restored afterwards."""
+    from artspeech_b200 import engine
+    lin = model.durationPredictor.duration_proj.linear_layer
+    old = lin.bias.detach().clone()
+    with torch.no_grad():
+        lin.bias += 1.67
+    model.invalidate_plans()
+    def run(bound):
+        syn = engine.Synthesizer(model, gen, device=dev, pipeline_depth=depth, max_graphs=64, duration_bound=bound)
+        wav_h = [torch.empty(B_PER_GPU, 2 * FRAMES * 300, dtype=torch.float32).pin_memory() for _ in range(depth + 1)]
+        len_h = [torch.zeros(B_PER_GPU, dtype=torch.int32).pin_memory() for _ in range(steps + 3 * N_INPUT_SETS)]
+        frames = []
+
+        def step(i, k):
+            t, m, _ = host_sets[i % N_INPUT_SETS]
+            wav, lens, _ = syn.synthesize(t, tok_lens, m, mel_lens, None)
+            with torch.cuda.stream(syn.last_stream):
+                wav_h[i % len(wav_h)][:, :wav.shape[1]].copy_(wav, non_blocking=True)
+                len_h[k].copy_(lens, non_blocking=True)      # frame counts travel with the waveforms
+        for i in range(3 * N_INPUT_SETS):                  # every input set in every pipeline slot: all buckets captured
+            step(i, steps + i)
+        syn.join()
+        torch.cuda.synchronize(dev)
+        captured = syn.stats["captures"]
+        e0, e1 = _events()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            step(i, i)
+        syn.join()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        audio = sum(int(v) for k in range(steps) for v in len_h[k].tolist()) * 300 / 24000.0
+        return {"value": audio / (ms / 1e3), "unit": "audio-s/s", "ms_per_step": ms / steps, "wall_ms_per_step": wall * 1e3 / steps,
+                "mean_audio_s_per_utterance": audio / (steps * B_PER_GPU), "graphs": captured,
+                "captures_in_timed_region": syn.stats["captures"] - captured}
+    try:
+        exact = run(None)
+        exact["note"] = ("graph A (encoders + predictor) -> device->host read-back of 16 frame counts -> graph B for the frame "
+                         "bucket the predictions land in")
+        bounded = run(4.0)
+        bounded["note"] = ("Synthesizer(duration_bound=4.0): ONE graph with the frame bucket tokens x 4 half-rate frames, no "
+                           "host synchronisation; tiles beyond an utterance's predicted length are skipped by the kernels")
+        return {"two_graphs_exact_bucket": exact, "one_graph_bounded_bucket": bounded,
+                "note": "end to end (pinned host inputs, D2H of waveforms and frame counts), durations predicted on the device"}
+    finally:
+        with torch.no_grad():
+            lin.bias.copy_(old)
+        model.invalidate_plans()
+
+
 def bench_config5(syn, dev, rank, world, dist, passes=2):
     """BASELINE config 5: 512 seeded mixed-length utterances, LPT-sharded over the run's N GPUs (strong scaling),
     each rank through engine.synthesize_many (length-bucketed micro-batches on bucketed CUDA graphs, waveforms
@@ -650,6 +708,7 @@ def run_ours(args):
             extras["config3"] = bench_config3(syn.generator, dev, pk)
             torch.cuda.empty_cache()
             extras["config4"] = bench_config4(syn, dev)
+            extras["predicted_durations"] = bench_predicted(model, gen, dev, host_sets, tok_lens, mel_lens, depth, args.steps)
 
     if rank != 0:
         if world > 1:

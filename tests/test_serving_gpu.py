@@ -266,3 +266,35 @@ def test_from_cache_is_bit_equal_to_fold_on_load(model_gpu, tmp_path):
     w2, _, _ = folded.synthesize(tok.to(DEV), [35, 20], mel.to(DEV), [110, 110], None)
     w3, _, _ = cached.synthesize(tok.to(DEV), [35, 20], mel.to(DEV), [110, 110], None)
     assert torch.equal(w2, w3)
+
+
+def test_bounded_single_graph_predicted_path(model_gpu):
+    """Synthesizer(duration_bound=...): predicted durations in ONE graph with a generous frame bucket (no host
+    synchronisation; the kernels skip the tiles beyond each utterance's length).  Waveforms and frame counts equal
+    the exact two-graph path; an utterance whose prediction exceeds the bound is re-run exactly by synthesize_many."""
+    from artspeech_b200 import engine
+    model, g, _, _ = model_gpu
+    gen = util.generator(0).to(DEV)
+    gsrc = torch.Generator().manual_seed(31)
+    tl = [40, 25, 33, 12]
+    toks = [torch.randint(1, 178, (t,), generator=gsrc) for t in tl]
+    mels = [(torch.randn(80, 110, generator=gsrc) * 0.5).clamp(-2, 2) for _ in tl]
+    exact = engine.Synthesizer(model, gen, device=DEV, use_cuda_graph=True)
+    w_ref, f_ref = engine.synthesize_many(exact, toks, mels, None, max_batch=4, to_host=True)
+    for bound in (4.0, 0.25):                                  # 0.25 frames per token: the longer utterances overflow
+        syn = engine.Synthesizer(model, gen, device=DEV, use_cuda_graph=True, duration_bound=bound, pipeline_depth=2,
+                                 frame_quantum=40 if bound == 4.0 else 8)
+        for _ in range(2):
+            w, f = engine.synthesize_many(syn, toks, mels, None, max_batch=4, to_host=True)
+        assert f == f_ref, (bound, f, f_ref)
+        for i in range(len(tl)):
+            assert w[i].numel() == 300 * f[i]
+            assert util.snr_db(w[i].float(), w_ref[i].float()) >= 50.0, (bound, i)
+        if bound == 4.0:
+            assert syn.stats["eager"] == 0 and syn.stats["captures"] <= 4
+            # direct call: sync-free, lengths on the device, zeros beyond each utterance's length
+            tok = torch.zeros(2, 40, dtype=torch.long); tok[0] = toks[0]; tok[1, :25] = toks[1]
+            wav, lens, _ = syn.synthesize(tok.to(DEV), [40, 25], torch.stack(mels[:2]).to(DEV), [110, 110], None)
+            syn.join()                                          # two batches in flight: the call ran on a slot stream
+            assert syn.last["frames"] is None and lens.tolist() == f_ref[:2]
+            assert float(wav[1, 300 * f_ref[1]:].abs().max()) == 0.0

@@ -12,6 +12,11 @@ gen = checkpoint.build_random_generator(0).to(dev).eval()
 g0 = torch.Generator().manual_seed(0)
 mel = torch.randn(16, 800, 80, generator=g0).clamp(-2, 2).to(dev).to(gen.compute_dtype)
 lens = torch.full((16,), 800, dtype=torch.int32, device=dev)
+if os.environ.get("RAGGED"):        # utterance lengths uniform in [50 %, 100 %] of the padded length, one full-length item
+    lens = torch.randint(400, 801, (16,), generator=g0).to(torch.int32)
+    lens[0] = 800
+    print("ragged lengths, valid fraction %.3f" % (lens.float().mean().item() / 800))
+    lens = lens.to(dev)
 variants = sys.argv[1:] or [""]
 graphs = []
 for v in variants:

@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([p.strip() for p in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.03)
 
     def stop(self):
         self._stop_evt.set()

@@ -286,12 +286,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 template <int H, int L256_NC>
-__global__ void __cluster_dims__(L256_NC, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(L256_NC, 1, 1) __launch_bounds__((H / L256_NC / 8) * 32, 1)
 bilstm_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
                       const float* __restrict__ whh_t /* [2][H][4H] */, int B, int T,
                       const int* __restrict__ lens, void* out, int odt, long long out_ld) {
   pdl_wait();   // programmatic dependent launch: everything above overlaps the previous kernel's tail
-  static_assert(H == 64 * L256_NC, "64 hidden units per CTA (8 warps x 8 units)");
+  constexpr int UPC = H / L256_NC;         // hidden units per CTA: one warp per 8 units (64 -> 8 warps, 128 -> 16 warps)
+  static_assert(UPC == 64 || UPC == 128, "8 or 16 warps per CTA");
   constexpr int G = 4 * H;
   constexpr int L256_HP = H + 8;   // padded pitch (halves) of the h tile
   constexpr int KSTEPS = H / 16;
@@ -303,7 +304,7 @@ bilstm_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const float* Wt = whh_t + (long long)dir * H * G;      // Wt[k][row]
-  const int unit = (int)crank * 64 + warp * 8 + gid;    // this thread's hidden unit
+  const int unit = (int)crank * UPC + warp * 8 + gid;   // this thread's hidden unit
 
   if (threadIdx.x < L256_NB) {
     const int b = b0 + threadIdx.x;
@@ -341,8 +342,8 @@ bilstm_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
   for (int i = 0; i < L256_NB; ++i) {
     const int b = b0 + i;
     if (b >= B) continue;
-    for (long long e = (long long)s_len[i] * 64 + threadIdx.x; e < (long long)T * 64; e += blockDim.x)
-      stany(out, ((long long)b * T + e / 64) * out_ld + dir * H + crank * 64 + (e % 64), 0.f, odt);
+    for (long long e = (long long)s_len[i] * UPC + threadIdx.x; e < (long long)T * UPC; e += blockDim.x)
+      stany(out, ((long long)b * T + e / UPC) * out_ld + dir * H + crank * UPC + (e % UPC), 0.f, odt);
   }
 
   auto xp_at = [&](int n, int len, int s, int gate) -> float {
@@ -368,7 +369,11 @@ bilstm_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
   for (int r = 0; r < L256_NC; ++r) raddr[r] = mapa_shared(smem_u32(&hs[0][pub_n][pub_unit]), (uint32_t)r);
   constexpr uint32_t BUF_BYTES = L256_NB * L256_HP * 2;
 
-  cluster_sync_all();   // every CTA has zeroed its tiles before anyone publishes into them
+  auto step_sync = [&]() {      // one CTA: a block barrier; a cluster: the h slices travel through DSMEM
+    if (L256_NC == 1) __syncthreads();
+    else cluster_sync_all();
+  };
+  step_sync();   // every CTA has zeroed its tiles before anyone publishes into them
 
   for (int s0 = 0; s0 < maxlen; s0 += PF) {
 #pragma unroll
@@ -410,7 +415,7 @@ bilstm_cluster_kernel(const float* __restrict__ xproj, long long xp_ld,
 #pragma unroll
         for (int r = 0; r < L256_NC; ++r) st_cluster_u32(raddr[r] + off, *reinterpret_cast<uint32_t*>(&pk2));
       }
-      cluster_sync_all();
+      step_sync();
     }
   }
 }
@@ -426,19 +431,30 @@ extern "C" int as_bilstm(const float* xproj, int64_t xproj_ld, const float* whh,
   ASB_REQUIRE(xproj && whh && out, AS_ERR_SHAPE, "as_bilstm: null pointer");
   ASB_REQUIRE(H == 128 || H == 256 || H == 64, AS_ERR_SHAPE, "as_bilstm: hidden size %d unsupported (64, 128 or 256)", H);
   if (H == 128) {
-    // the 2-CTA cluster split (64 units per CTA, h exchanged through DSMEM) halves the instructions per thread and step
-    // but was measured SLOWER (B200: 1.15 vs 1.02 us per step at B = 16, 1.59 vs 1.00 at 8 x 4800): the step is
-    // bound by its dependency chain (8 chained mma + MUFU chain + one barrier) and a cluster barrier costs more than
-    // __syncthreads.  ASB_LSTM128_CLUSTER=1 selects it for experiments.
-    static const bool cluster2 = getenv("ASB_LSTM128_CLUSTER") != nullptr;
-    if (!cluster2) {
-      dim3 grid128((B + L128_NB - 1) / L128_NB, 2);
-      ASB_CUDA(launch_k(bilstm128_mma_kernel, grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+    // Round-2 experiments on the step time (B200, B = 16, T = 800; 8 x 4800), all SLOWER or equal to the 8-warp kernel's
+    // 1.02 / 1.00 us per step, so it stays the default:
+    //   * ASB_LSTM128=16warp: 16 warps in one CTA (bilstm_cluster_kernel<128, 1>, a warp per 8 hidden units, half the
+    //     instructions per thread): 1.13 / 1.34 us;
+    //   * ASB_LSTM128=cluster: 2-CTA cluster, h exchanged through DSMEM: 1.15 / 1.59 us (a cluster barrier per step);
+    //   * two accumulator sets per gate (HMMA chain 4 deep instead of 8): 1.04 / 1.04 us.
+    // ncu (profiles/r02_ncu_full_bilstm128_8warp.txt): 286 instructions per warp-step at 30 % issue utilisation, tensor
+    // pipe 27 %, dominant stall "wait" -- the step is a ~2000-cycle dependency chain (operand loads -> 8 chained HMMA ->
+    // MUFU chain -> h store -> barrier) that neither more warps nor a shorter HMMA chain shortened.
+    static const char* mode = getenv("ASB_LSTM128");
+    if (mode != nullptr && strcmp(mode, "16warp") == 0) {
+      dim3 grid((B + L256_NB - 1) / L256_NB, 2);
+      ASB_CUDA(launch_k(bilstm_cluster_kernel<128, 1>, grid, 512, 0, reinterpret_cast<cudaStream_t>(stream),
           xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
       return AS_OK;
     }
-    dim3 grid(2 * ((B + L256_NB - 1) / L256_NB), 2);
-    ASB_CUDA(launch_k(bilstm_cluster_kernel<128, 2>, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+    if (mode != nullptr && strcmp(mode, "cluster") == 0) {
+      dim3 grid(2 * ((B + L256_NB - 1) / L256_NB), 2);
+      ASB_CUDA(launch_k(bilstm_cluster_kernel<128, 2>, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+          xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
+      return AS_OK;
+    }
+    dim3 grid128((B + L128_NB - 1) / L128_NB, 2);
+    ASB_CUDA(launch_k(bilstm128_mma_kernel, grid128, 256, 0, reinterpret_cast<cudaStream_t>(stream),
         xproj, xproj_ld, whh, B, T, lens, out, out_dtype, out_ld));
     return AS_OK;
   }

@@ -39,6 +39,17 @@ class _Captured:
         self.uid = 0
 
 
+class _Ticket:
+    """A call issued with ``synthesize(..., defer=True)``: with predicted durations everything up to the frame-count
+    read-back is enqueued; ``Synthesizer.finish`` synchronises on it and enqueues the rest."""
+    __slots__ = ("result", "last", "last_stream", "slot", "run_stream", "is_side", "ent", "got", "B", "launches")
+
+    def __init__(self):
+        self.result = self.last = self.last_stream = self.ent = self.got = self.run_stream = None
+        self.slot = self.B = self.launches = 0
+        self.is_side = False
+
+
 class Synthesizer:
     """Text -> waveform for batches of utterances on one GPU.
 
@@ -282,7 +293,7 @@ class Synthesizer:
     # ---------------------------------------------------------------------------------------
     @torch.no_grad()
     def synthesize(self, tokens, tok_lens, mels, mel_lens, durations=None, voice=None, predict_durations: bool = False,
-                   exact_frames: bool = False):
+                   exact_frames: bool = False, defer: bool = False):
         """``tokens`` int64 [B,Tt] and ``mels`` fp32 [B,80,Tr]: device tensors or (pinned) HOST tensors -- host inputs
         are copied straight into the graph's static buffers; ``tok_lens`` / ``mel_lens`` int64 [B] HOST tensors (or
         lists); ``durations`` int64 [B,Tt] HOST tensor or None (predict them, one device->host sync of B integers);
@@ -291,7 +302,10 @@ class Synthesizer:
         ``Tm_max`` the longest utterance's frame count; per-call extras (predicted durations, frame counts) are in
         ``self.last``.  With ``duration_bound`` set and no ``durations`` the pass is sync-free: ``Tm_max`` is then the
         bound's frame bucket and the utterances' true lengths are the returned ``mel_lengths`` (``exact_frames=True``
-        forces the two-graph path with the frame-count read-back)."""
+        forces the two-graph path with the frame-count read-back).
+        ``defer=True`` returns a ticket instead of the result; ``finish(ticket)`` completes the call.  With predicted
+        durations the ticket is handed out BEFORE the host waits for the frame counts, so a caller can issue the next
+        call's graph A first (``synthesize_many`` does): the GPU then always has work queued while the host wakes up."""
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         self.last_stream = cur
@@ -321,7 +335,8 @@ class Synthesizer:
             self._seen[key_a] = n
             graphable = n >= self.capture_after
         if not graphable:
-            return self._eager(tokens, tl, mels, ml, durations, voice, predict)
+            res = self._eager(tokens, tl, mels, ml, durations, voice, predict)
+            return self._done_ticket(res) if defer else res
         if self._epoch != nn_util.plan_epoch():
             self.drop_graphs()
 
@@ -378,24 +393,14 @@ class Synthesizer:
                 # the only device->host hand-off of the pass: B frame counts (the other slot keeps the GPU busy)
                 pin_sum = ent.pin_meta[:B]
                 pin_sum.copy_(ent.state["pred_sum"], non_blocking=True)
-                got = torch.cuda.Event()
-                got.record(run_stream)
-                got.synchronize()
-                sums = [int(v) for v in pin_sum.tolist()]
-                L_b = _ceil_to(max(sums), self.frame_quantum)
-                key_b = ("b", ent.uid, L_b)
-                eb = self._lookup(slot, key_b)
-                if eb is None:
-                    eb = _Captured()
-                    eb.state = ent
-                    st = ent.state
-                    eb.graph, eb.out, eb.launches = self._capture(slot, lambda: self._phase_b(st, st["pred_dur"], L_b))
-                    self._insert(slot, key_b, eb)
-                eb.graph.replay()
-                launches += eb.launches
-                out = eb.out
-            else:
-                out = ent.out
+                t = _Ticket()
+                t.got = torch.cuda.Event()
+                t.got.record(run_stream)
+                t.slot, t.run_stream, t.is_side, t.ent, t.B, t.launches = slot, run_stream, run_stream is not cur, ent, B, launches
+                if defer:
+                    return t
+                return self.finish(t)
+            out = ent.out
             if run_stream is not cur:
                 done = torch.cuda.Event()
                 done.record(run_stream)
@@ -406,11 +411,54 @@ class Synthesizer:
         ops._count(launches)
         if bounded:
             self.last = dict(out, frames=None, graph=True, frame_bound=2 * key_a[-1])
-            return out["wav"], out["mel_lengths"], out["mel"]
+            res = (out["wav"], out["mel_lengths"], out["mel"])
+        else:
+            Tm = 2 * max(sums)
+            self.last = dict(out, frames=[2 * v for v in sums], graph=True)
+            res = (out["wav"][:, :HOP * Tm], out["mel_lengths"], out["mel"][:, :, :Tm])
+        return self._done_ticket(res) if defer else res
+
+    def _done_ticket(self, res):
+        t = _Ticket()
+        t.result, t.last, t.last_stream = res, self.last, self.last_stream
+        return t
+
+    def finish(self, ticket: "_Ticket"):
+        """Complete a deferred call: -> (wav, mel_lengths, mel) as ``synthesize`` returns them; sets ``last`` /
+        ``last_stream`` for this call."""
+        if ticket.result is not None:
+            self.last, self.last_stream = ticket.last, ticket.last_stream
+            return ticket.result
+        ent, slot, B = ticket.ent, ticket.slot, ticket.B
+        with torch.cuda.stream(ticket.run_stream):
+            ticket.got.synchronize()
+            sums = [int(v) for v in ent.pin_meta[:B].tolist()]
+            L_b = _ceil_to(max(sums), self.frame_quantum)
+            key_b = ("b", ent.uid, L_b)
+            eb = self._lookup(slot, key_b)
+            if eb is None:
+                eb = _Captured()
+                eb.state = ent
+                st = ent.state
+                eb.graph, eb.out, eb.launches = self._capture(slot, lambda: self._phase_b(st, st["pred_dur"], L_b))
+                self._insert(slot, key_b, eb)
+            eb.graph.replay()
+            out = eb.out
+            if ticket.is_side:
+                done = torch.cuda.Event()
+                done.record(ticket.run_stream)
+                self._slot_done[slot] = done
+        launches = ticket.launches + eb.launches
+        self.stats["replays"] += 1
+        self.last_stream = ticket.run_stream
+        self.launches_per_call = launches
+        ops._count(launches)
         Tm = 2 * max(sums)
-        self.last = dict(out, frames=[2 * v for v in sums], graph=True,
-                         duration=(ent.state or ent.out)["duration"], pred_dur=(ent.state or ent.out)["pred_dur"])
-        return out["wav"][:, :HOP * Tm], out["mel_lengths"], out["mel"][:, :, :Tm]
+        self.last = dict(out, frames=[2 * v for v in sums], graph=True, duration=ent.state["duration"],
+                         pred_dur=ent.state["pred_dur"])
+        ticket.result, ticket.last, ticket.last_stream = (out["wav"][:, :HOP * Tm], out["mel_lengths"], out["mel"][:, :, :Tm]), \
+            self.last, self.last_stream
+        return ticket.result
 
     def join(self):
         """Make the current stream wait for every pipelined call issued so far."""
@@ -540,20 +588,10 @@ def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels
     if to_host:
         arena.reset()
     pending, late = [], []
-    for idx in bucket_utterances(plan_frames, max_batch, max_padded_frames, quantum=2 * syn.frame_quantum):
-        Tt = max(int(tokens[i].shape[0]) for i in idx)
-        Tr = max(int(ref_mels[i].shape[1]) for i in idx)
-        tok = torch.zeros(len(idx), Tt, dtype=torch.long).pin_memory()
-        dur = torch.zeros(len(idx), Tt, dtype=torch.long) if durations is not None else None
-        mel = torch.zeros(len(idx), ref_mels[idx[0]].shape[0], Tr).pin_memory()
-        for j, i in enumerate(idx):
-            tok[j, :tokens[i].shape[0]] = tokens[i]
-            if dur is not None:
-                dur[j, :durations[i].shape[0]] = durations[i]
-            mel[j, :, :ref_mels[i].shape[1]] = ref_mels[i]
-        tl = [int(tokens[i].shape[0]) for i in idx]
-        ml = [int(ref_mels[i].shape[1]) for i in idx]
-        wav, mel_lengths, _ = syn.synthesize(tok, tl, mel, ml, dur)
+
+    def collect(idx, ticket):
+        """Finish a deferred call and queue the copies of its waveforms (on the call's stream)."""
+        wav, mel_lengths, _ = syn.finish(ticket)
         got = syn.last["frames"]
         if got is not None:
             for j, i in enumerate(idx):
@@ -574,7 +612,30 @@ def synthesize_many(syn: "Synthesizer", tokens: Sequence[torch.Tensor], ref_mels
             else:
                 for j, i in enumerate(idx):
                     wavs[i] = dst[j, :HOP * frames[i]] if to_host else wav[j, :HOP * frames[i]].clone()
+
+    # With predicted durations a call synchronises on its frame counts between its two graphs: issue the NEXT
+    # micro-batch's first graph before finishing the current one (one call of look-ahead; needs a second pipeline slot)
+    lookahead = 1 if syn.pipeline_depth >= 2 else 0
+    waiting = []
+    for idx in bucket_utterances(plan_frames, max_batch, max_padded_frames, quantum=2 * syn.frame_quantum):
+        Tt = max(int(tokens[i].shape[0]) for i in idx)
+        Tr = max(int(ref_mels[i].shape[1]) for i in idx)
+        tok = torch.zeros(len(idx), Tt, dtype=torch.long).pin_memory()
+        dur = torch.zeros(len(idx), Tt, dtype=torch.long) if durations is not None else None
+        mel = torch.zeros(len(idx), ref_mels[idx[0]].shape[0], Tr).pin_memory()
+        for j, i in enumerate(idx):
+            tok[j, :tokens[i].shape[0]] = tokens[i]
+            if dur is not None:
+                dur[j, :durations[i].shape[0]] = durations[i]
+            mel[j, :, :ref_mels[i].shape[1]] = ref_mels[i]
+        tl = [int(tokens[i].shape[0]) for i in idx]
+        ml = [int(ref_mels[i].shape[1]) for i in idx]
+        waiting.append((idx, syn.synthesize(tok, tl, mel, ml, dur, defer=True)))
+        while len(waiting) > lookahead:
+            collect(*waiting.pop(0))
         pending.append((tok, mel))            # pinned inputs must outlive their asynchronous copies
+    while waiting:
+        collect(*waiting.pop(0))
     syn.join()
     if to_host or late:
         torch.cuda.current_stream(syn.device).synchronize()

@@ -402,14 +402,28 @@ def bench_predicted(model, gen, dev, host_sets, tok_lens, mel_lens, depth, steps
         len_h = [torch.zeros(B_PER_GPU, dtype=torch.int32).pin_memory() for _ in range(steps + 3 * N_INPUT_SETS)]
         frames = []
 
-        def step(i, k):
-            t, m, _ = host_sets[i % N_INPUT_SETS]
-            wav, lens, _ = syn.synthesize(t, tok_lens, m, mel_lens, None)
+        waiting = []
+
+        def collect(i, k, ticket):
+            wav, lens, _ = syn.finish(ticket)
             with torch.cuda.stream(syn.last_stream):
                 wav_h[i % len(wav_h)][:, :wav.shape[1]].copy_(wav, non_blocking=True)
                 len_h[k].copy_(lens, non_blocking=True)      # frame counts travel with the waveforms
+
+        def step(i, k):
+            # one call of look-ahead: the next batch's graph A is enqueued before the host waits for this batch's frame
+            # counts (engine.synthesize(defer=True) / finish), as engine.synthesize_many does
+            t, m, _ = host_sets[i % N_INPUT_SETS]
+            waiting.append((i, k, syn.synthesize(t, tok_lens, m, mel_lens, None, defer=True)))
+            while len(waiting) > (1 if depth >= 2 else 0):
+                collect(*waiting.pop(0))
+
+        def drain():
+            while waiting:
+                collect(*waiting.pop(0))
         for i in range(3 * N_INPUT_SETS):                  # every input set in every pipeline slot: all buckets captured
             step(i, steps + i)
+        drain()
         syn.join()
         torch.cuda.synchronize(dev)
         captured = syn.stats["captures"]
@@ -418,6 +432,7 @@ def bench_predicted(model, gen, dev, host_sets, tok_lens, mel_lens, depth, steps
         e0.record()
         for i in range(steps):
             step(i, i)
+        drain()
         syn.join()
         e1.record()
         torch.cuda.synchronize(dev)

@@ -283,6 +283,18 @@ def bench_config1(model, gen, dev):
         call(None)
     forced = _median([call(dur)[0] for _ in range(15)])
     pred = [call(None) for _ in range(15)]
+    # the same with the reference voice's style-encoder outputs cached (engine.encode_voice)
+    voice = syn.encode_voice(mel.to(dev), ml)
+
+    def call_voice():
+        t0 = time.perf_counter()
+        wav, _, _ = syn.synthesize(tok_p, tl, mel_p, ml, dur, voice=voice, predict_durations=True)
+        wav_h[:, :wav.shape[1]].copy_(wav, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return (time.perf_counter() - t0) * 1e3
+    for _ in range(3):
+        call_voice()
+    cached = _median([call_voice() for _ in range(15)])
     # acoustic model alone (to the mel): its own graph
     tok_d, mel_d = tok.to(dev), mel.to(dev)
     tl_d, ml_d, dur_d = tl.to(dev), ml.to(dev), dur.to(dev)
@@ -316,6 +328,7 @@ def bench_config1(model, gen, dev):
         first.append((time.perf_counter() - t0) * 1e3)
     return {"workload": "1 utterance, 120 phonemes, 3 s reference mel, 800 frames = 10 s (forced) / predicted",
             "ms_to_mel": to_mel, "ms_to_waveform": forced, "audio_s_per_s": AUDIO_S_PER_UTT / (forced / 1e3),
+            "ms_to_waveform_voice_cached": cached,
             "ms_to_waveform_predicted_durations": _median([p[0] for p in pred]),
             "predicted_audio_s": pred[0][1] / 24000.0,
             "stream_first_chunk_ms_after_mel": _median(first[2:]),

@@ -129,6 +129,40 @@ def test_conv_igemm_2cta_pairs(shape, dt):
     _close(out16, ref16, 1e-2 if dt == torch.bfloat16 else 2e-3, "raw16")
 
 
+def test_conv_igemm_2cta_full_ring_two_streams():
+    """The CTA-pair implicit GEMM with its ring running full: an epilogue-bound launch (fp32 residual in, fp32 raw + f16
+    activated out: acoustic AdainResBlk convs) repeated back to back on one stream while a second stream keeps the GPU
+    busy.  With a 6-stage ring this raised a sticky 'illegal memory access' within ~500 launches (DESIGN.md section 4b);
+    the ring is capped at 4 stages.  6000 launches, then the result against the fp32 model."""
+    torch.manual_seed(21)
+    B, T, C = 16, 800, 512
+    x = torch.randn(B, T, C).to(torch.float16)
+    w = torch.randn(3, C, C) / (3 * C) ** 0.5
+    bias = torch.randn(C) * 0.1
+    res = torch.randn(B, T, C)
+    lens = torch.full((B,), T, dtype=torch.int32)
+    packs = {d: ops.pack_conv(w, bias, ops.taps_1d(3, 1), torch.float16, d) for d in ("cpu", DEV)}
+    ref_raw, ref_act = sim.conv(x, packs["cpu"], res1=res, raw=torch.float32, act_out=torch.float16, act=ops.ACT_LRELU,
+                                slope=0.2, lens=lens)
+    xg, rg, lg = x.to(DEV), res.to(DEV), lens.to(DEV)
+    raw = torch.empty(B, T, C, device=DEV)
+    act = torch.empty(B, T, C, device=DEV, dtype=torch.float16)
+    big = torch.randn(32 << 20, device=DEV)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for i in range(1500):
+        with torch.cuda.stream(sa):
+            big.mul_(1.0)
+        with torch.cuda.stream(sb):
+            for _ in range(4):
+                ops.conv(xg, packs[DEV], res1=rg, raw=raw, act_out=act, act=ops.ACT_LRELU, slope=0.2, lens=lg)
+        if i % 100 == 99:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    _close(raw, ref_raw, 2e-3)
+    _close(act, ref_act, 4e-3)
+
+
 @pytest.mark.parametrize("shape", [(2, 70, 80, 64, 64, 3, 3), (1, 33, 40, 128, 128, 3, 3), (2, 50, 10, 64, 128, 3, 3),
                                    (1, 15, 5, 512, 512, 5, 5)])
 def test_conv_igemm_2d(shape):

@@ -298,3 +298,31 @@ def test_bounded_single_graph_predicted_path(model_gpu):
             syn.join()                                          # two batches in flight: the call ran on a slot stream
             assert syn.last["frames"] is None and lens.tolist() == f_ref[:2]
             assert float(wav[1, 300 * f_ref[1]:].abs().max()) == 0.0
+
+
+def test_pipelined_step_soak(model_gpu):
+    """300 back-to-back pipelined steps at the benchmark's shape (two graphs in flight, inputs changing every call) end
+    without a sticky CUDA error and still give the first call's waveform for the first inputs.  Regression test for the
+    CTA-pair implicit GEMM's ring depth (with a 6-stage ring this loop died within ~200 steps)."""
+    import bench
+    from artspeech_b200 import engine
+    model, g, sd, dist_cpu = model_gpu
+    gen = util.generator(0).to(DEV)
+    syn = engine.Synthesizer(model, gen, device=DEV, use_cuda_graph=True, pipeline_depth=2)
+    sets = [bench.make_inputs(0, 16, i) for i in range(4)]
+    dev_sets = [(t.to(DEV), m.to(DEV), d) for t, _, m, _, d in sets]
+    tl, ml = sets[0][1], sets[0][3]
+    first = None
+    for i in range(300):
+        t, m, d = dev_sets[i % 4]
+        wav, _, _ = syn.synthesize(t, tl, m, ml, d, predict_durations=True)
+        if i == 0:
+            syn.join()
+            first = wav.clone()
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+    t, m, d = dev_sets[0]
+    wav, _, _ = syn.synthesize(t, tl, m, ml, d, predict_durations=True)
+    syn.join()
+    torch.cuda.synchronize()
+    assert torch.equal(wav, first)

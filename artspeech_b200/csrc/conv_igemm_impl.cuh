@@ -32,6 +32,7 @@ struct ConvArgs {
   int epi_tma;             // 1: all-16-bit 1-D epilogue through shared memory + TMA
   int halo_baseoff;        // swizzled halo: put (row & 7) into the descriptor's base-offset field
   int skip;                // 1: tiles that lie entirely beyond their item's length are left out (conv_igemm / 2cta only)
+  int pad_stages;          // CTA-pair kernel experiments: unused ring-stage-sized blocks in front of the ring (ASB_2CTA_PAD)
 };
 
 struct EpiMaps { CUtensorMap r1, raw, act; };
@@ -610,7 +611,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   constexpr int TMEM_COLS = 512;
 
   extern __shared__ unsigned char smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t smem_base = ((smem_u32(smem_dyn) + 1023u) & ~1023u) + (uint32_t)a.pad_stages * STAGE_BYTES;   // pad: experiments
   const int S = a.stages;
   const uint32_t bar_base = smem_base + S * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -1056,10 +1057,12 @@ int launch_conv_2cta(const CUtensorMap& tmA, const CUtensorMap& tmWh, const EpiM
   if (stages > max_stages) stages = max_stages;
   if (stages < 2) stages = 2;
   a.stages = stages;
+  static const int pad = getenv("ASB_2CTA_PAD") ? atoi(getenv("ASB_2CTA_PAD")) : 0;
+  a.pad_stages = (stages + pad) * STAGE_BYTES <= budget ? pad : 0;
   a.idesc = (a.idesc & ~(0x1Fu << 24)) | (uint32_t(256 >> 4) << 24);      // UMMA M = 256 across the CTA pair
   static const bool no_skip = getenv("ASB_CONV_NO_SKIP") != nullptr;
   a.skip = (a.lens != nullptr && !no_skip) ? 1 : 0;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
+  const size_t smem = (size_t)(stages + a.pad_stages) * STAGE_BYTES + 8 * (2 * stages + 6) + (size_t)a.CoutP * 4 + 1024 + 16 +
                       (a.epi_tma ? epi_bytes(BN) + 1024 : 0);
   ASB_SMEM_OPT_IN(227 * 1024, conv_igemm_2cta_kernel<BK, BF16>);
   const int m_tiles = a.B * a.n_ttiles * a.n_ftiles;

@@ -29,11 +29,11 @@ def _ceil_to(v: int, q: int) -> int:
 
 class _Captured:
     """One captured CUDA graph with its static inputs / outputs (all owned by the graph's memory pool)."""
-    __slots__ = ("graph", "tok", "mels", "voice", "meta", "dur", "lens_t", "pin_meta", "pin_free", "out", "launches",
-                 "state", "uid")
+    __slots__ = ("graph", "tok", "mels", "voice", "meta", "dur", "lens_t", "mel_lens", "pin_meta", "pin_free", "out",
+                 "launches", "state", "uid")
 
     def __init__(self):
-        self.graph = self.tok = self.mels = self.voice = self.meta = self.dur = self.lens_t = None
+        self.graph = self.tok = self.mels = self.voice = self.meta = self.dur = self.lens_t = self.mel_lens = None
         self.pin_meta = self.pin_free = self.out = self.state = None
         self.launches = 0
         self.uid = 0
@@ -352,6 +352,7 @@ class Synthesizer:
         if ent is None:
             ent = self._static_inputs(B, Tt_b, mels, voice)
             mel_lens_dev = torch.full((B,), Tr, dtype=torch.int64, device=dev)
+            ent.mel_lens = mel_lens_dev                 # a graph input like the others: lives as long as the graph
             if durations is not None:
                 L_b = key_a[-1]
 

@@ -243,6 +243,17 @@ def bench_vocoder_roofline(syn, mel_static, lens_static, dev, steps):
         vg.replay()
     torch.cuda.synchronize(dev)
     e0, e1 = _events()
+    # best of 10 single replays after one idle second: how MEASURED_PEAKS.json's burst peak itself was taken (best of
+    # 10 sub-millisecond GEMMs on an idle GPU); the SM clock drops within ~0.3 s of sustained load
+    time.sleep(1.0)
+    singles = []
+    for _ in range(10):
+        e0.record()
+        vg.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        singles.append(e0.elapsed_time(e1))
+    bench_vocoder_roofline.best_ms = min(singles)
     reps = max(10, steps)
     e0.record()
     for _ in range(reps):
@@ -654,6 +665,11 @@ def run_ours(args):
             "traffic": vocoder_traffic(),
             "peak_source": pk["source"] + " BURST bf16 (the kernel family timed alone, graph replay, %.0f ms)" % (voc_ms * max(10, args.steps)),
             "flops_per_step": voc_flops, "vocoder_ms": voc_ms, "vocoder_share_of_step": voc_ms / (ms / args.steps),
+            "best_of_10_after_idle": {"vocoder_ms": bench_vocoder_roofline.best_ms,
+                                      "achieved": voc_flops / bench_vocoder_roofline.best_ms / 1e9,
+                                      "frac": voc_flops / bench_vocoder_roofline.best_ms / 1e9 / pk["bf16_tflops"],
+                                      "note": "single graph replays after 1 s idle, best of 10: the protocol of the burst peak "
+                                              "itself; 'achieved' above is the mean over back-to-back replays on the loaded GPU"},
             "sustained": {"achieved": sustained, "peak": pk["bf16_tflops_sustained"],
                           "frac": sustained / pk["bf16_tflops_sustained"], "vocoder_ms": voc_long_ms,
                           "loop_s": voc_long_ms * long_reps / 1e3,

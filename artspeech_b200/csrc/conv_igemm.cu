@@ -216,7 +216,28 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
   static const bool no_epi_tma = getenv("ASB_NO_EPI_TMA") != nullptr;
   a.epi_tma = (!no_epi_tma && a.fast && p->F == 1 && p->Fo == 1 && a.k_res2 == 0 && a.k_res1 != 2 && a.k_raw != 2 &&
                a.k_act != 2 && (a.k_raw == 1 || a.k_act == 1)) ? 1 : 0;
-  if (a.epi_tma) {
+  // ... or (epi_tma = 2, wide layers only: never a halo kernel) fp32 residual and / or fp32 raw output next to an optional
+  // 16-bit activated output: the residual stream between AdaIN blocks.  ASB_NO_EPI_TMA32=1 keeps the direct epilogue.
+  static const bool no_epi_tma32 = getenv("ASB_NO_EPI_TMA32") != nullptr;
+  if (!a.epi_tma && !no_epi_tma && !no_epi_tma32 && a.fast && p->F == 1 && p->Fo == 1 && a.k_res2 == 0 && bn >= 128 &&
+      p->Cin > 128 && a.k_res1 != 1 && a.k_raw != 1 && a.k_act != 2 && (a.k_res1 == 2 || a.k_raw == 2)) {
+    auto mk32 = [&](CUtensorMap* m, const void* ptr, long long ld, bool f32) -> bool {
+      const cuuint64_t es_b = f32 ? 4 : 2;
+      cuuint64_t dims[3] = {(cuuint64_t)p->Cout, (cuuint64_t)p->To, (cuuint64_t)p->B};
+      cuuint64_t strides[2] = {(cuuint64_t)ld * es_b, (cuuint64_t)ld * es_b * p->To};
+      cuuint32_t box[3] = {32, 32, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = true;
+    if (a.k_res1 == 2) ok = ok && mk32(&em.r1, p->res1, p->res1_ld, true);
+    if (a.k_raw == 2) ok = ok && mk32(&em.raw, p->y_raw, p->y_raw_ld, true);
+    if (a.k_act == 1) ok = ok && mk32(&em.act, p->y_act, p->y_act_ld, false);
+    if (ok) a.epi_tma = 2;
+  }
+  if (a.epi_tma == 1) {
     auto mk = [&](CUtensorMap* m, const void* ptr, long long ld) -> bool {
       cuuint64_t dims[3] = {(cuuint64_t)p->Cout, (cuuint64_t)p->To, (cuuint64_t)p->B};
       cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * p->To};

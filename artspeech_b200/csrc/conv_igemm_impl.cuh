@@ -337,27 +337,33 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
 // accumulator wait), raw / activated outputs leave by TMA store.  Out-of-range rows / channels are
 // clipped by the TMA unit, so partial tiles need no special path.
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool BF16>
+template <int BN, bool BF16, bool F32 = false>
 __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMaps& maps, uint32_t tmem_base,
                                                  uint32_t tfull0, uint32_t tempty0, int warp, int lane, int m_tiles,
                                                  int total_tiles, const float* bias_s, uint32_t epi_base,
                                                  int tile_first = -1, int tile_step = 0, int cl = 1, int rank = 0,
                                                  bool remote_tempty = false) {
+  // F32 (epi_tma == 2): the residual and / or the raw output are fp32 (the residual stream between AdaIN blocks), the
+  // activated output 16-bit.  Groups of 32 channels: fp32 tiles of [32 rows][32 ch] (128 B rows, 128B swizzle), the
+  // activated tile [32][32] 16-bit (64 B rows, 64B swizzle).  The direct epilogue these launches used before had every
+  // lane store its own row (32 wavefronts per instruction) and ran 60-70 % slower than the MMAs.
   if (tile_first < 0) { tile_first = blockIdx.x; tile_step = gridDim.x; }
   const int ew = warp - 2;                 // 0..7
   const int wg = ew >> 2;
   const int q = warp & 3;
-  constexpr uint32_t EPC = epi_cols(BN);                  // channels per staged group
-  constexpr uint32_t ROWB = EPC * 2u;                     // bytes per staged row (128 or 64)
-  constexpr uint32_t TILEB = 32u * ROWB;
+  constexpr uint32_t EPC = F32 ? 32u : epi_cols(BN);      // channels per staged group
+  constexpr uint32_t ROWA = F32 ? 128u : EPC * 2u;        // bytes per staged row of the residual / raw tile
+  constexpr uint32_t ROWB = EPC * 2u;                     // ... of the activated tile (16-bit)
+  constexpr uint32_t TILEA = 32u * ROWA;
   constexpr int CPG = EPC / 16;                           // 16-channel chunks per group
   const uint32_t bufA = epi_base + (uint32_t)ew * epi_warp_bytes(BN);   // residual in / raw out (in place)
-  const uint32_t bufB = bufA + TILEB;                                    // activated out
+  const uint32_t bufB = bufA + epi_warp_bytes(BN) / 2u;                  // activated out
   const uint32_t rbar = epi_base + 8u * epi_warp_bytes(BN) + 8u * ew;
-  const bool has_r1 = a.k_res1 == 1, has_raw = a.k_raw == 1, has_act = a.k_act == 1;
-  const uint32_t rowoff = (uint32_t)lane * ROWB;
+  const bool has_r1 = a.k_res1 != 0, has_raw = a.k_raw != 0, has_act = a.k_act != 0;
+  const uint32_t rowoffA = (uint32_t)lane * ROWA, rowoffB = (uint32_t)lane * ROWB;
   // 16-byte unit swizzle of the TMA layout: 128B mode XORs with (row & 7), 64B mode with (row >> 1) & 3
-  const uint32_t sw = (EPC == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+  const uint32_t swA = (ROWA == 128) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+  const uint32_t swB = (ROWB == 128) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
   uint32_t rphase = 0;
   int lt_live = 0;
   for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -379,7 +385,7 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
 
     if (has_r1 && lane == 0 && ngroups > 0) {
       bulk_wait_read0();                                   // previous stores have drained this buffer
-      mbar_expect_tx(rbar, TILEB);
+      mbar_expect_tx(rbar, TILEA);
       tma_load_3d(bufA, &maps.r1, rbar, n0, t_base, b);
     }
     mbar_wait(tfull0 + 8u * wg, ((uint32_t)lt >> 1) & 1u);
@@ -408,19 +414,42 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
             v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
           }
-          const uint32_t o0 = rowoff + (((uint32_t)(2 * cc) ^ sw) << 4), o1 = rowoff + (((uint32_t)(2 * cc + 1) ^ sw) << 4);
-          if (has_r1) {
-            const uint4 t0 = lds128(bufA + o0), t1 = lds128(bufA + o1);
-            unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
-            unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
-            unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
-            unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
-          }
+          if constexpr (F32) {
+            // fp32 tile: this row's 16 channels are 4 units of 16 bytes
+            uint32_t oa[4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * scale;
-          if (has_raw) {
-            sts128(bufA + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
-            sts128(bufA + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+            for (int j = 0; j < 4; ++j) oa[j] = bufA + rowoffA + (((uint32_t)(4 * cc + j) ^ swA) << 4);
+            if (has_r1) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 t4 = lds128(oa[j]);
+                v[4 * j] += __uint_as_float(t4.x); v[4 * j + 1] += __uint_as_float(t4.y);
+                v[4 * j + 2] += __uint_as_float(t4.z); v[4 * j + 3] += __uint_as_float(t4.w);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * scale;
+            if (has_raw) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(oa[j], make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                         __float_as_uint(v[4 * j + 3])));
+            }
+          } else {
+            const uint32_t o0 = rowoffA + (((uint32_t)(2 * cc) ^ swA) << 4), o1 = rowoffA + (((uint32_t)(2 * cc + 1) ^ swA) << 4);
+            if (has_r1) {
+              const uint4 t0 = lds128(bufA + o0), t1 = lds128(bufA + o1);
+              unpack_add<BF16>(t0.x, v[0], v[1]); unpack_add<BF16>(t0.y, v[2], v[3]);
+              unpack_add<BF16>(t0.z, v[4], v[5]); unpack_add<BF16>(t0.w, v[6], v[7]);
+              unpack_add<BF16>(t1.x, v[8], v[9]); unpack_add<BF16>(t1.y, v[10], v[11]);
+              unpack_add<BF16>(t1.z, v[12], v[13]); unpack_add<BF16>(t1.w, v[14], v[15]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = masked ? 0.f : v[i] * scale;
+            if (has_raw) {
+              sts128(bufA + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+              sts128(bufA + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+            }
           }
           if (has_act) {
             if (a.act_simple) {
@@ -430,8 +459,9 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.act, a.slope);
             }
-            sts128(bufB + o0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
-            sts128(bufB + o1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
+            const uint32_t b0 = bufB + rowoffB + (((uint32_t)(2 * cc) ^ swB) << 4), b1 = bufB + rowoffB + (((uint32_t)(2 * cc + 1) ^ swB) << 4);
+            sts128(b0, make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7])));
+            sts128(b1, make_uint4(pack2<BF16>(v[8], v[9]), pack2<BF16>(v[10], v[11]), pack2<BF16>(v[12], v[13]), pack2<BF16>(v[14], v[15])));
           }
         }
       }
@@ -443,7 +473,7 @@ __device__ __forceinline__ void run_epilogue_tma(const ConvArgs& a, const EpiMap
         bulk_commit();
         if (has_r1 && g + 1 < ngroups) {
           bulk_wait_read0();
-          mbar_expect_tx(rbar, TILEB);
+          mbar_expect_tx(rbar, TILEA);
           tma_load_3d(bufA, &maps.r1, rbar, n0 + (g + 1) * (int)EPC, t_base, b);
         }
       }
@@ -572,7 +602,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===== epilogue =====
-    if (a.epi_tma)
+    if (a.epi_tma == 2) {
+      if constexpr (BN >= 128)
+        run_epilogue_tma<BN, BF16, true>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
+    } else if (a.epi_tma)
       run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s, epi_base);
     else
       run_epilogue<BN, BF16>(a, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, m_tiles, total_tiles, bias_s);
@@ -711,7 +744,10 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else {
     // ===== epilogue (both CTAs, each on its own 128 rows): arrives on the leader's tempty barriers =====
     const uint32_t tempty_leader = mapa_u32(tempty_bar(0), 0);
-    if (a.epi_tma)
+    if (a.epi_tma == 2)
+      run_epilogue_tma<BN, BF16, true>(a, emaps, tmem_base, tfull_bar(0), tempty_leader, warp, lane, m_pairs, total_super, bias_s,
+                                       epi_base, cid, n_clusters, 2, (int)rank, true);
+    else if (a.epi_tma)
       run_epilogue_tma<BN, BF16>(a, emaps, tmem_base, tfull_bar(0), tempty_leader, warp, lane, m_pairs, total_super, bias_s, epi_base,
                                  cid, n_clusters, 2, (int)rank, true);
     else

@@ -129,6 +129,43 @@ def test_conv_igemm_2cta_pairs(shape, dt):
     _close(out16, ref16, 1e-2 if dt == torch.bfloat16 else 2e-3, "raw16")
 
 
+@pytest.mark.parametrize("shape", [(2, 300, 256, 520, 3, 1), (3, 95, 512, 648, 1, 1), (16, 150, 512, 512, 5, 1),
+                                   (1, 700, 1216, 1024, 3, 1), (4, 333, 192, 392, 3, 2)])
+@pytest.mark.parametrize("kinds", ["res+raw+act", "raw", "res+act", "res+raw"])
+def test_conv_fp32_tma_epilogue(shape, kinds):
+    """fp32 residual in / fp32 raw out (+ 16-bit activated out) on wide layers: the TMA epilogue with 32-channel fp32
+    tiles (epi_tma = 2).  Output widths that are not multiples of 16 / 32 / the tile, small problems (128-wide tiles),
+    ragged lengths, a scale, and strided (channel-slice) outputs."""
+    B, T, Cin, Cout, k, dil = shape
+    torch.manual_seed(17)
+    dt = torch.float16
+    x = (torch.randn(B, T, Cin) * 0.5).to(dt)
+    w = torch.randn(k, Cout, Cin) / (Cin * k) ** 0.5
+    bias = torch.randn(Cout)
+    r1 = torch.randn(B, T, Cout) if "res" in kinds else None
+    lens = _lens(B, T)
+    pw_c = ops.pack_conv(w, bias, ops.taps_1d(k, dil), dt, "cpu")
+    pw_g = ops.pack_conv(w, bias, ops.taps_1d(k, dil), dt, DEV)
+    want_raw = torch.float32 if "raw" in kinds else None
+    want_act = dt if "act" in kinds else None
+    ref_raw, ref_act = sim.conv(x, pw_c, res1=r1, scale=0.7, raw=want_raw, act_out=want_act, act=ops.ACT_LRELU, slope=0.2, lens=lens)
+    # outputs as channel slices of wider buffers (row stride > Cout), as the decoder's concatenated inputs are written
+    wide_raw = torch.full((B, T, Cout + 24), 7.0, device=DEV) if want_raw is not None else None
+    wide_act = torch.full((B, T, Cout + 40), 7.0, device=DEV, dtype=dt) if want_act is not None else None
+    raw, act = ops.conv(x.to(DEV), pw_g, res1=None if r1 is None else r1.to(DEV), scale=0.7,
+                        raw=None if wide_raw is None else wide_raw[..., 8:8 + Cout],
+                        act_out=None if wide_act is None else wide_act[..., 16:16 + Cout],
+                        act=ops.ACT_LRELU, slope=0.2, lens=lens.to(DEV))
+    if want_raw is not None:
+        _close(raw, ref_raw, 2e-4, "raw")
+        assert float(wide_raw[..., :8].min()) == 7.0 and float(wide_raw[..., 8 + Cout:].min()) == 7.0   # neighbours untouched
+        for b in range(B):
+            assert torch.count_nonzero(raw[b, int(lens[b]):]) == 0
+    if want_act is not None:
+        _close(act, ref_act, 2e-3, "act")
+        assert float(wide_act[..., :16].float().min()) == 7.0 and float(wide_act[..., 16 + Cout:].float().min()) == 7.0
+
+
 def test_conv_igemm_2cta_full_ring_two_streams():
     """The CTA-pair implicit GEMM with its ring running full: an epilogue-bound launch (fp32 residual in, fp32 raw + f16
     activated out: acoustic AdainResBlk convs) repeated back to back on one stream while a second stream keeps the GPU

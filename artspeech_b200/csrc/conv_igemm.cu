@@ -220,7 +220,7 @@ extern "C" int as_conv_igemm(const as_conv_params* p, void* stream) {
   // 16-bit activated output: the residual stream between AdaIN blocks.  ASB_NO_EPI_TMA32=1 keeps the direct epilogue.
   static const bool no_epi_tma32 = getenv("ASB_NO_EPI_TMA32") != nullptr;
   if (!a.epi_tma && !no_epi_tma && !no_epi_tma32 && a.fast && p->F == 1 && p->Fo == 1 && a.k_res2 == 0 && bn >= 128 &&
-      p->Cin > 128 && a.k_res1 != 1 && a.k_raw != 1 && a.k_act != 2 && (a.k_res1 == 2 || a.k_raw == 2)) {
+      (p->Cin > 128 || p->CoutP > 128) && a.k_res1 != 1 && a.k_raw != 1 && a.k_act != 2 && (a.k_res1 == 2 || a.k_raw == 2)) {
     auto mk32 = [&](CUtensorMap* m, const void* ptr, long long ld, bool f32) -> bool {
       const cuuint64_t es_b = f32 ? 4 : 2;
       cuuint64_t dims[3] = {(cuuint64_t)p->Cout, (cuuint64_t)p->To, (cuuint64_t)p->B};

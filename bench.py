@@ -87,36 +87,48 @@ def make_config5(n_utts: int = 512, seed: int = 0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons while the timed region runs: ONE background `nvidia-smi -lms 100` process, as
+    in B200_PROFILING.md (a process per sample took driver locks often enough to slow the end-to-end arm on a busy
+    box).  Started early so that it is already sampling; `begin()` marks the start of the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.samples, self.t0, self.proc = index, [], 0.0, None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([p.strip() for p in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.03)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append((time.time(), parts))
+        except Exception:
+            pass
+
+    def begin(self):
+        self.t0 = time.time()
 
     def stop(self):
-        self._stop_evt.set()
+        t1 = time.time()
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+        except Exception:
+            pass
         self.join(timeout=3)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = max([int(s[1]) for s in self.samples if s[1].isdigit()] or [0])
+        inside = [s for t, s in self.samples if self.t0 <= t <= t1 + 0.15]
+        if not inside:                      # a very short timed region: the samples nearest to it
+            inside = [s for t, s in self.samples if t >= self.t0 - 0.3]
+        sm = sorted(int(s[0]) for s in inside if s[0].isdigit())
+        mx = max([int(s[1]) for s in inside if s[1].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in inside for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(self.samples)}
-
-
+                "samples": len(inside)}
 
 
 def vocoder_traffic():
@@ -542,6 +554,9 @@ def run_ours(args):
     depth = 1 if args.no_graph else args.pipeline
     syn = engine.Synthesizer(model, gen, device=dev, use_cuda_graph=not args.no_graph, pipeline_depth=depth)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                 # nvidia-smi needs a moment to come up: running well before the timed region
     sets = [make_inputs(rank, B_PER_GPU, i) for i in range(N_INPUT_SETS)]
     tok_lens, mel_lens = sets[0][1], sets[0][3]
     dev_sets = [(t.to(dev), m.to(dev), d) for t, _, m, _, d in sets]
@@ -601,9 +616,8 @@ def run_ours(args):
 
     # inputs (tokens 19 KB + mels 1.2 MB) are tiny, but every step streams > 10 GB of activations
     # through HBM, far beyond the 126 MB L2: no explicit flush needed between timed iterations.
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.begin()
     l0 = ops.launch_count
     ms = timed(step_resident, args.steps)
     launches = ops.launch_count - l0
